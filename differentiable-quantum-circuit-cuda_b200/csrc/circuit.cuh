@@ -1,0 +1,377 @@
+// Circuit executor: the B200 counterpart of the reference's Rust `Circuit`
+// (/root/reference/src/circuit.rs:86-430) and `QuantizedTensor`
+// (src/quantized_tensor.rs:54-238), behind the C ABI of include/qdc_circuit.h.
+//
+// Differences that matter on B200 (design, not semantics):
+//  * two resident 2^n buffers (state + adjoint) instead of four
+//    (src/circuit.rs:96-102, 276, 396-398): |0..0> is generated, not stored,
+//    and the density seed is fused so no transient `bwd_addition` exists;
+//  * every density / gradient lands in one device-resident double buffer that
+//    is copied back ONCE per call (the reference does cudaMalloc + blocking
+//    D2H + cudaFree per gradient, src/primitives.cu:264-291);
+//  * the backward step of a gate is one 4*S kernel (engine.cuh) instead of
+//    three 2*S kernels (src/circuit.rs:320-333).
+#pragma once
+#include <string>
+#include <vector>
+
+#include "engine.cuh"
+
+enum Kind {
+  K_CONST_Q2 = 0, K_VAR_Q2, K_CONST_Q2_NONU, K_VAR_Q2_NONU, K_CONST_Q2_DIAG, K_VAR_Q2_DIAG,
+  K_CONST_Q1, K_CONST_Q1_NONU, K_VAR_Q1, K_VAR_Q1_NONU,
+  K_Q2_DENS, K_Q1_DENS, K_DIFF_Q2_DENS, K_DIFF_Q1_DENS
+};
+
+static inline bool kind_is_gate(int k) { return k <= K_VAR_Q1_NONU; }
+static inline bool kind_is_var(int k) {
+  return k == K_VAR_Q2 || k == K_VAR_Q2_NONU || k == K_VAR_Q2_DIAG || k == K_VAR_Q1 || k == K_VAR_Q1_NONU;
+}
+static inline bool kind_is_nonu(int k) {
+  return k == K_CONST_Q2_NONU || k == K_VAR_Q2_NONU || k == K_CONST_Q1_NONU || k == K_VAR_Q1_NONU;
+}
+static inline bool kind_is_diag(int k) { return k == K_CONST_Q2_DIAG || k == K_VAR_Q2_DIAG; }
+static inline bool kind_is_q1(int k) { return k >= K_CONST_Q1 && k <= K_VAR_Q1_NONU; }
+static inline bool kind_is_q2dense(int k) { return k <= K_VAR_Q2_NONU; }
+static inline bool kind_is_dens(int k) { return k >= K_Q2_DENS; }
+static inline bool kind_is_diff_dens(int k) { return k == K_DIFF_Q2_DENS || k == K_DIFF_Q1_DENS; }
+static inline bool kind_is_q1_dens(int k) { return k == K_Q1_DENS || k == K_DIFF_Q1_DENS; }
+static inline int kind_gate_len(int k) { return kind_is_q2dense(k) ? 16 : 4; }
+static inline int kind_dens_len(int k) { return kind_is_q1_dens(k) ? 4 : 16; }
+
+struct Inst {
+  int kind;
+  int pos2, pos1;  // q1 kinds use pos2 only
+};
+
+struct Stats {
+  uint64_t kernel_launches = 0, hbm_passes = 0, algorithmic_bytes = 0;
+};
+
+struct GateList {
+  const cplx_t* flat;
+  const uint32_t* lens;
+  size_t count;
+};
+
+class Circuit {
+ public:
+  explicit Circuit(int n) : n_(n) {}
+  ~Circuit() { release(); }
+
+  int n_;
+  std::vector<Inst> insts_;
+  cplx_t* state_ = nullptr;
+  cplx_t* bwd_ = nullptr;
+  cplx_t* initial_ = nullptr;  // nullptr <=> |0..0>
+  Workspace ws_;
+  double* d_res_ = nullptr;  // device results: 32 doubles per slot
+  size_t d_res_slots_ = 0;
+  std::vector<double> h_res_;
+  cudaStream_t stream_ = 0;
+  Stats stats_;
+  int opt_fuse_ = 0;
+
+  void release() {
+    if (state_) cudaFree(state_);
+    if (bwd_) cudaFree(bwd_);
+    if (initial_) cudaFree(initial_);
+    if (d_res_) cudaFree(d_res_);
+    state_ = bwd_ = initial_ = nullptr;
+    d_res_ = nullptr;
+    d_res_slots_ = 0;
+    ws_release(ws_);
+  }
+
+  size_t bytes() const { return sizeof(cplx_t) << n_; }
+
+  const char* ensure_state() {
+    if (!state_) QDC_CUDA(cudaMalloc((void**)&state_, bytes()));
+    return nullptr;
+  }
+
+  const char* ensure_results(size_t slots) {
+    if (slots > d_res_slots_) {
+      if (d_res_) QDC_CUDA(cudaFree(d_res_));
+      QDC_CUDA(cudaMalloc((void**)&d_res_, slots * 32 * sizeof(double)));
+      d_res_slots_ = slots;
+    }
+    h_res_.resize(slots * 32);
+    return nullptr;
+  }
+
+  const char* set_state_from_host(const cplx_t* host, size_t len) {
+    if (len == 0 || (len & (len - 1)) != 0) return qdc_errf("State size is not a power of 2.");
+    if (len != ((size_t)1 << n_))
+      return qdc_errf("Size of the given state does not match the size of the tensor.");
+    if (!initial_) QDC_CUDA(cudaMalloc((void**)&initial_, bytes()));
+    QDC_CUDA(cudaMemcpy(initial_, host, bytes(), cudaMemcpyHostToDevice));
+    return nullptr;
+  }
+
+  const char* add(int kind, size_t pos2, size_t pos1) {
+    if (kind < 0 || kind > K_DIFF_Q1_DENS) return qdc_errf("Unknown instruction kind %d.", kind);
+    const bool one = kind_is_q1(kind) || kind_is_q1_dens(kind);
+    if (one) {
+      if (pos2 >= (size_t)n_) return qdc_errf("pos is out of the bound.");
+    } else {
+      if (pos1 == pos2) return qdc_errf("pos1 and pos2 must be different.");
+      if (pos1 >= (size_t)n_) return qdc_errf("pos1 is out of the bound.");
+      if (pos2 >= (size_t)n_) return qdc_errf("pos2 is out of the bound.");
+    }
+    insts_.push_back(Inst{kind, (int)pos2, one ? -1 : (int)pos1});
+    return nullptr;
+  }
+
+  size_t count(int what) const {
+    size_t c = 0;
+    for (const Inst& in : insts_) {
+      const int k = in.kind;
+      switch (what) {
+        case 0: c++; break;
+        case 1: c += kind_is_gate(k) && !kind_is_var(k); break;
+        case 2: c += kind_is_gate(k) && kind_is_var(k); break;
+        case 3: c += kind_is_dens(k); break;
+        case 4: c += kind_is_diff_dens(k); break;
+        case 5: c += kind_is_dens(k) ? kind_dens_len(k) : 0; break;
+        case 6: c += kind_is_diff_dens(k) ? kind_dens_len(k) : 0; break;
+        case 7: c += (kind_is_gate(k) && kind_is_var(k)) ? kind_gate_len(k) : 0; break;
+      }
+    }
+    return c;
+  }
+
+  // Pair every gate instruction with its matrix (front-pop order of
+  // src/circuit.rs:171-200, 222-251; equivalently the back-pop order of :278+).
+  const char* bind_gates(const GateList& cg, const GateList& vg, std::vector<const cplx_t*>& ptr,
+                         bool backward) {
+    ptr.assign(insts_.size(), nullptr);
+    size_t ci = 0, vi = 0, coff = 0, voff = 0;
+    for (size_t i = 0; i < insts_.size(); i++) {
+      const int k = insts_[i].kind;
+      if (!kind_is_gate(k)) continue;
+      const bool var = kind_is_var(k);
+      const GateList& gl = var ? vg : cg;
+      size_t& idx = var ? vi : ci;
+      size_t& off = var ? voff : coff;
+      if (idx >= gl.count) {
+        if (backward) return qdc_errf("The number of gates is less than required.");
+        return qdc_errf("The number of %s gates is less than required.", var ? "variable" : "constant");
+      }
+      if ((int)gl.lens[idx] != kind_gate_len(k)) return qdc_errf("Incorrect len of the gate's buffer.");
+      ptr[i] = gl.flat + off;
+      off += gl.lens[idx];
+      idx++;
+    }
+    if (ci != cg.count) return qdc_errf("Number of constant gates is more than required.");
+    if (vi != vg.count)
+      return qdc_errf(backward ? "Number of constant gates is more than required."
+                               : "Number of variable gates is more than required.");
+    return nullptr;
+  }
+
+  void account(uint64_t launches, uint64_t passes, uint64_t alg_passes) {
+    stats_.kernel_launches += launches;
+    stats_.hbm_passes += passes;
+    stats_.algorithmic_bytes += alg_passes * (uint64_t)bytes();
+  }
+
+  const char* reset_state() {
+    QDC_TRY(ensure_state());
+    if (initial_) {
+      QDC_TRY(eng_copy(stream_, initial_, state_, n_));  // data_transfer, src/circuit.rs:174,225
+    } else {
+      QDC_TRY(eng_set_standard(stream_, state_, n_));
+      account(1, 0, 0);
+    }
+    return nullptr;
+  }
+
+  // ------------------------------------------------------------- forward
+  const char* sweep(const GateList& cg, const GateList& vg, bool all_dens, cplx_t* out, size_t cap,
+                    size_t* out_len) {
+    if (insts_.empty()) return qdc_errf("The circuit is empty.");
+    stats_ = Stats();
+    std::vector<const cplx_t*> gp;
+    QDC_TRY(bind_gates(cg, vg, gp, false));
+    const size_t need = count(all_dens ? 5 : 6);
+    if (cap < need) return qdc_errf("Output buffer too small: %zu < %zu.", cap, need);
+    const size_t nslots = count(all_dens ? 3 : 4);
+    QDC_TRY(ensure_results(nslots));
+    QDC_TRY(reset_state());
+    QDC_TRY(run_forward(gp, all_dens));
+    // single read-back of every density
+    if (nslots) {
+      QDC_CUDA(cudaMemcpyAsync(h_res_.data(), d_res_, nslots * 32 * sizeof(double), cudaMemcpyDeviceToHost,
+                               stream_));
+    }
+    QDC_CUDA(cudaStreamSynchronize(stream_));
+    size_t slot = 0, o = 0;
+    for (const Inst& in : insts_) {
+      if (!kind_is_dens(in.kind)) continue;
+      if (!all_dens && !kind_is_diff_dens(in.kind)) continue;
+      const double* h = &h_res_[slot * 32];
+      if (kind_is_q1_dens(in.kind)) {
+        for (int i = 0; i < 4; i++) {
+          out[o + i].x = (real_t)h[2 * i];
+          out[o + i].y = (real_t)h[2 * i + 1];
+        }
+        o += 4;
+      } else {
+        zc m[16];
+        unpermute_q2(h, in.pos2 < in.pos1, m);
+        for (int i = 0; i < 16; i++) {
+          out[o + i].x = (real_t)m[i].real();
+          out[o + i].y = (real_t)m[i].imag();
+        }
+        o += 16;
+      }
+      slot++;
+    }
+    *out_len = o;
+    return nullptr;
+  }
+
+  const char* run_forward(const std::vector<const cplx_t*>& gp, bool all_dens) {
+    size_t slot = 0;
+    for (size_t i = 0; i < insts_.size(); i++) {
+      const Inst& in = insts_[i];
+      const int k = in.kind;
+      if (kind_is_q1(k)) {
+        QDC_TRY(eng_q1gate(stream_, ws_, state_, gp[i], FORM_PLAIN, in.pos2, n_));
+        account(1, 1, 2);
+      } else if (kind_is_q2dense(k)) {
+        QDC_TRY(eng_q2gate(stream_, ws_, state_, gp[i], FORM_PLAIN, in.pos2, in.pos1, n_));
+        account(1, 1, 2);
+      } else if (kind_is_diag(k)) {
+        QDC_TRY(eng_q2diag(stream_, ws_, state_, gp[i], false, in.pos2, in.pos1, n_));
+        account(1, 1, 2);
+      } else {
+        if (!all_dens && !kind_is_diff_dens(k)) continue;
+        double* dst = d_res_ + slot * 32;
+        if (kind_is_q1_dens(k)) {
+          QDC_TRY(eng_dens_q1(stream_, ws_, state_, in.pos2, n_, dst));
+        } else {
+          QDC_TRY(eng_dens_q2(stream_, ws_, state_, in.pos2, in.pos1, n_, dst));
+        }
+        account(2, 1, 1);
+        slot++;
+      }
+    }
+    return nullptr;
+  }
+
+  // ------------------------------------------------------------ backward
+  const char* backward(const GateList& dg, const GateList& cg, const GateList& vg, cplx_t* out, size_t cap,
+                       size_t* out_len) {
+    if (insts_.empty()) return qdc_errf("The circuit is empty.");
+    if (!state_) return qdc_errf("backward() called before forward().");
+    stats_ = Stats();
+    std::vector<const cplx_t*> gp;
+    QDC_TRY(bind_gates(cg, vg, gp, true));
+    // cotangents: one per Diff* density, program order
+    std::vector<const cplx_t*> dp(insts_.size(), nullptr);
+    {
+      size_t di = 0, off = 0;
+      for (size_t i = 0; i < insts_.size(); i++) {
+        if (!kind_is_diff_dens(insts_[i].kind)) continue;
+        if (di >= dg.count)
+          return qdc_errf("The number of gradients wrt density matrices is less than required.");
+        if ((int)dg.lens[di] != kind_dens_len(insts_[i].kind))
+          return qdc_errf("Incorrect len of the gate's buffer.");
+        dp[i] = dg.flat + off;
+        off += dg.lens[di];
+        di++;
+      }
+      if (di != dg.count) return qdc_errf("Number of gradients wrt density matrices is more than required.");
+    }
+    const size_t need = count(7);
+    if (cap < need) return qdc_errf("Output buffer too small: %zu < %zu.", cap, need);
+    const size_t nvar = count(2);
+    QDC_TRY(ensure_results(nvar));
+    if (nvar) QDC_CUDA(cudaMemsetAsync(d_res_, 0, nvar * 32 * sizeof(double), stream_));
+    if (!bwd_) QDC_CUDA(cudaMalloc((void**)&bwd_, bytes()));
+
+    // variable-gate slot of every instruction
+    std::vector<long> vslot(insts_.size(), -1);
+    {
+      long s = 0;
+      for (size_t i = 0; i < insts_.size(); i++)
+        if (kind_is_gate(insts_[i].kind) && kind_is_var(insts_[i].kind)) vslot[i] = s++;
+    }
+    QDC_TRY(run_backward(gp, dp, vslot));
+    if (nvar) {
+      QDC_CUDA(cudaMemcpyAsync(h_res_.data(), d_res_, nvar * 32 * sizeof(double), cudaMemcpyDeviceToHost,
+                               stream_));
+    }
+    QDC_CUDA(cudaStreamSynchronize(stream_));
+    size_t o = 0;
+    for (size_t i = 0; i < insts_.size(); i++) {
+      if (vslot[i] < 0) continue;
+      const Inst& in = insts_[i];
+      const double* h = &h_res_[(size_t)vslot[i] * 32];
+      if (kind_is_q2dense(in.kind)) {
+        zc m[16];
+        unpermute_q2(h, in.pos2 < in.pos1, m);
+        for (int j = 0; j < 16; j++) {
+          out[o + j].x = (real_t)m[j].real();
+          out[o + j].y = (real_t)m[j].imag();
+        }
+        o += 16;
+      } else {
+        for (int j = 0; j < 4; j++) {
+          out[o + j].x = (real_t)h[2 * j];
+          out[o + j].y = (real_t)h[2 * j + 1];
+        }
+        o += 4;
+      }
+    }
+    *out_len = o;
+    return nullptr;
+  }
+
+  const char* run_backward(const std::vector<const cplx_t*>& gp, const std::vector<const cplx_t*>& dp,
+                           const std::vector<long>& vslot) {
+    bool live = false;  // is there an adjoint yet? (bwd_option, src/circuit.rs:276)
+    for (size_t ii = insts_.size(); ii-- > 0;) {
+      const Inst& in = insts_[ii];
+      const int k = in.kind;
+      if (k == K_Q1_DENS || k == K_Q2_DENS) continue;
+      if (k == K_DIFF_Q1_DENS) {
+        QDC_TRY(eng_seed_q1(stream_, ws_, state_, bwd_, dp[ii], in.pos2, n_, live));
+        account(1, 1, live ? 3 : 2);
+        live = true;
+        continue;
+      }
+      if (k == K_DIFF_Q2_DENS) {
+        QDC_TRY(eng_seed_q2(stream_, ws_, state_, bwd_, dp[ii], in.pos2, in.pos1, n_, live));
+        account(1, 1, live ? 3 : 2);
+        live = true;
+        continue;
+      }
+      const int inv_form = kind_is_nonu(k) ? FORM_INV : FORM_CONJ_TR;
+      double* gdst = (vslot[ii] >= 0) ? d_res_ + (size_t)vslot[ii] * 32 : nullptr;
+      if (!live) {
+        // no adjoint yet: un-compute only; variable gates keep their zero gradient
+        if (kind_is_q1(k)) {
+          QDC_TRY(eng_q1gate(stream_, ws_, state_, gp[ii], inv_form, in.pos2, n_));
+        } else if (kind_is_q2dense(k)) {
+          QDC_TRY(eng_q2gate(stream_, ws_, state_, gp[ii], inv_form, in.pos2, in.pos1, n_));
+        } else {
+          QDC_TRY(eng_q2diag(stream_, ws_, state_, gp[ii], true, in.pos2, in.pos1, n_));
+        }
+        account(1, 1, 2);
+        continue;
+      }
+      if (kind_is_q1(k)) {
+        QDC_TRY(eng_rev_q1(stream_, ws_, state_, bwd_, gp[ii], inv_form, in.pos2, n_, gdst));
+      } else if (kind_is_q2dense(k)) {
+        QDC_TRY(eng_rev_q2(stream_, ws_, state_, bwd_, gp[ii], inv_form, in.pos2, in.pos1, n_, gdst));
+      } else {
+        QDC_TRY(eng_rev_diag(stream_, ws_, state_, bwd_, gp[ii], in.pos2, in.pos1, n_, gdst));
+      }
+      account(gdst ? 2 : 1, 2, 4);
+    }
+    return nullptr;
+  }
+};
