@@ -63,6 +63,9 @@ _CIRCUIT_SIGNATURES = {
     "qdc_circuit_set_stream": (_err, [C.c_void_p, C.c_void_p]),
     "qdc_circuit_set_option": (_err, [C.c_void_p, C.c_char_p, C.c_long]),
     "qdc_circuit_last_stats": (_err, [C.c_void_p, C.c_void_p]),
+    "qdc_profile_categories": (C.c_int, []),
+    "qdc_profile_category_name": (C.c_char_p, [C.c_int]),
+    "qdc_circuit_last_profile": (_err, [C.c_void_p, C.c_int, C.c_void_p]),
     "qdc_reverse_step": (_err, [c_cplx_p, c_cplx_p, c_cplx_p, c_cplx_p, C.c_int, C.c_int, _sz, _sz, _sz]),
     "qdc_density_seed": (_err, [c_cplx_p, c_cplx_p, c_cplx_p, C.c_int, C.c_int, _sz, _sz, _sz]),
 }
@@ -77,6 +80,10 @@ class QdcError(RuntimeError):
 class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("hbm_passes", C.c_uint64),
                 ("algorithmic_bytes", C.c_uint64)]
+
+
+class ProfileEntry(C.Structure):
+    _fields_ = [("launches", C.c_uint64), ("ms", C.c_double), ("algorithmic_bytes", C.c_uint64)]
 
 
 def lib_path(precision: str) -> str:

@@ -54,6 +54,77 @@ struct GateList {
   size_t count;
 };
 
+// Per-category device timing with CUDA events on the executing stream
+// (enabled by option "profile"); feeds bench.py's roofline block.
+enum ProfCat {
+  CAT_FWD_Q1 = 0, CAT_FWD_Q2, CAT_FWD_DIAG, CAT_DENSITY, CAT_SEED, CAT_UNCOMPUTE, CAT_REV_Q1, CAT_REV_Q2,
+  CAT_REV_DIAG, CAT_REV_CONST, CAT_TILE_FWD, CAT_TILE_BWD, CAT_EXCHANGE, CAT_COUNT
+};
+static const char* const kProfCatNames[CAT_COUNT] = {
+    "fwd_q1", "fwd_q2", "fwd_diag", "density", "seed", "uncompute", "rev_q1", "rev_q2",
+    "rev_diag", "rev_const", "tile_fwd", "tile_bwd", "exchange"};
+
+struct ProfEntry {
+  uint64_t launches = 0;
+  double ms = 0;
+  uint64_t alg_bytes = 0;
+};
+
+struct Profiler {
+  bool on = false;
+  std::vector<cudaEvent_t> pool;
+  size_t used = 0;
+  struct Rec { int cat; cudaEvent_t a, b; uint64_t bytes; };
+  std::vector<Rec> recs;
+  ProfEntry cats[CAT_COUNT];
+  cudaEvent_t get() {
+    if (used == pool.size()) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      pool.push_back(e);
+    }
+    return pool[used++];
+  }
+  void reset() {
+    used = 0;
+    recs.clear();
+    for (auto& c : cats) c = ProfEntry();
+  }
+  cudaEvent_t begin(cudaStream_t st) {
+    cudaEvent_t a = get();
+    cudaEventRecord(a, st);
+    return a;
+  }
+  void end(cudaStream_t st, int cat, cudaEvent_t a, uint64_t bytes) {
+    cudaEvent_t b = get();
+    cudaEventRecord(b, st);
+    recs.push_back(Rec{cat, a, b, bytes});
+  }
+  void collect() {  // after the stream has been synchronised
+    for (const Rec& r : recs) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, r.a, r.b);
+      cats[r.cat].launches++;
+      cats[r.cat].ms += ms;
+      cats[r.cat].alg_bytes += r.bytes;
+    }
+    recs.clear();
+    used = 0;
+  }
+  ~Profiler() {
+    for (cudaEvent_t e : pool) cudaEventDestroy(e);
+  }
+};
+
+// PROF(cat, algorithmic passes, launch expression)
+#define PROF(cat, alg_passes, expr)                                           \
+  do {                                                                        \
+    cudaEvent_t pa_ = nullptr;                                                \
+    if (prof_.on) pa_ = prof_.begin(stream_);                                 \
+    QDC_TRY(expr);                                                            \
+    if (prof_.on) prof_.end(stream_, cat, pa_, (uint64_t)(alg_passes) * bytes()); \
+  } while (0)
+
 class Circuit {
  public:
   explicit Circuit(int n) : n_(n) {}
@@ -71,6 +142,7 @@ class Circuit {
   cudaStream_t stream_ = 0;
   Stats stats_;
   int opt_fuse_ = 0;
+  Profiler prof_;
 
   void release() {
     if (state_) cudaFree(state_);
@@ -192,6 +264,7 @@ class Circuit {
                     size_t* out_len) {
     if (insts_.empty()) return qdc_errf("The circuit is empty.");
     stats_ = Stats();
+    prof_.reset();
     std::vector<const cplx_t*> gp;
     QDC_TRY(bind_gates(cg, vg, gp, false));
     const size_t need = count(all_dens ? 5 : 6);
@@ -206,6 +279,7 @@ class Circuit {
                                stream_));
     }
     QDC_CUDA(cudaStreamSynchronize(stream_));
+    if (prof_.on) prof_.collect();
     size_t slot = 0, o = 0;
     for (const Inst& in : insts_) {
       if (!kind_is_dens(in.kind)) continue;
@@ -238,21 +312,21 @@ class Circuit {
       const Inst& in = insts_[i];
       const int k = in.kind;
       if (kind_is_q1(k)) {
-        QDC_TRY(eng_q1gate(stream_, ws_, state_, gp[i], FORM_PLAIN, in.pos2, n_));
+        PROF(CAT_FWD_Q1, 2, eng_q1gate(stream_, ws_, state_, gp[i], FORM_PLAIN, in.pos2, n_));
         account(1, 1, 2);
       } else if (kind_is_q2dense(k)) {
-        QDC_TRY(eng_q2gate(stream_, ws_, state_, gp[i], FORM_PLAIN, in.pos2, in.pos1, n_));
+        PROF(CAT_FWD_Q2, 2, eng_q2gate(stream_, ws_, state_, gp[i], FORM_PLAIN, in.pos2, in.pos1, n_));
         account(1, 1, 2);
       } else if (kind_is_diag(k)) {
-        QDC_TRY(eng_q2diag(stream_, ws_, state_, gp[i], false, in.pos2, in.pos1, n_));
+        PROF(CAT_FWD_DIAG, 2, eng_q2diag(stream_, ws_, state_, gp[i], false, in.pos2, in.pos1, n_));
         account(1, 1, 2);
       } else {
         if (!all_dens && !kind_is_diff_dens(k)) continue;
         double* dst = d_res_ + slot * 32;
         if (kind_is_q1_dens(k)) {
-          QDC_TRY(eng_dens_q1(stream_, ws_, state_, in.pos2, n_, dst));
+          PROF(CAT_DENSITY, 1, eng_dens_q1(stream_, ws_, state_, in.pos2, n_, dst));
         } else {
-          QDC_TRY(eng_dens_q2(stream_, ws_, state_, in.pos2, in.pos1, n_, dst));
+          PROF(CAT_DENSITY, 1, eng_dens_q2(stream_, ws_, state_, in.pos2, in.pos1, n_, dst));
         }
         account(2, 1, 1);
         slot++;
@@ -267,6 +341,7 @@ class Circuit {
     if (insts_.empty()) return qdc_errf("The circuit is empty.");
     if (!state_) return qdc_errf("backward() called before forward().");
     stats_ = Stats();
+    prof_.reset();
     std::vector<const cplx_t*> gp;
     QDC_TRY(bind_gates(cg, vg, gp, true));
     // cotangents: one per Diff* density, program order
@@ -305,6 +380,7 @@ class Circuit {
                                stream_));
     }
     QDC_CUDA(cudaStreamSynchronize(stream_));
+    if (prof_.on) prof_.collect();
     size_t o = 0;
     for (size_t i = 0; i < insts_.size(); i++) {
       if (vslot[i] < 0) continue;
@@ -338,13 +414,13 @@ class Circuit {
       const int k = in.kind;
       if (k == K_Q1_DENS || k == K_Q2_DENS) continue;
       if (k == K_DIFF_Q1_DENS) {
-        QDC_TRY(eng_seed_q1(stream_, ws_, state_, bwd_, dp[ii], in.pos2, n_, live));
+        PROF(CAT_SEED, live ? 3 : 2, eng_seed_q1(stream_, ws_, state_, bwd_, dp[ii], in.pos2, n_, live));
         account(1, 1, live ? 3 : 2);
         live = true;
         continue;
       }
       if (k == K_DIFF_Q2_DENS) {
-        QDC_TRY(eng_seed_q2(stream_, ws_, state_, bwd_, dp[ii], in.pos2, in.pos1, n_, live));
+        PROF(CAT_SEED, live ? 3 : 2, eng_seed_q2(stream_, ws_, state_, bwd_, dp[ii], in.pos2, in.pos1, n_, live));
         account(1, 1, live ? 3 : 2);
         live = true;
         continue;
@@ -354,21 +430,24 @@ class Circuit {
       if (!live) {
         // no adjoint yet: un-compute only; variable gates keep their zero gradient
         if (kind_is_q1(k)) {
-          QDC_TRY(eng_q1gate(stream_, ws_, state_, gp[ii], inv_form, in.pos2, n_));
+          PROF(CAT_UNCOMPUTE, 2, eng_q1gate(stream_, ws_, state_, gp[ii], inv_form, in.pos2, n_));
         } else if (kind_is_q2dense(k)) {
-          QDC_TRY(eng_q2gate(stream_, ws_, state_, gp[ii], inv_form, in.pos2, in.pos1, n_));
+          PROF(CAT_UNCOMPUTE, 2, eng_q2gate(stream_, ws_, state_, gp[ii], inv_form, in.pos2, in.pos1, n_));
         } else {
-          QDC_TRY(eng_q2diag(stream_, ws_, state_, gp[ii], true, in.pos2, in.pos1, n_));
+          PROF(CAT_UNCOMPUTE, 2, eng_q2diag(stream_, ws_, state_, gp[ii], true, in.pos2, in.pos1, n_));
         }
         account(1, 1, 2);
         continue;
       }
       if (kind_is_q1(k)) {
-        QDC_TRY(eng_rev_q1(stream_, ws_, state_, bwd_, gp[ii], inv_form, in.pos2, n_, gdst));
+        PROF(gdst ? CAT_REV_Q1 : CAT_REV_CONST, 4,
+             eng_rev_q1(stream_, ws_, state_, bwd_, gp[ii], inv_form, in.pos2, n_, gdst));
       } else if (kind_is_q2dense(k)) {
-        QDC_TRY(eng_rev_q2(stream_, ws_, state_, bwd_, gp[ii], inv_form, in.pos2, in.pos1, n_, gdst));
+        PROF(gdst ? CAT_REV_Q2 : CAT_REV_CONST, 4,
+             eng_rev_q2(stream_, ws_, state_, bwd_, gp[ii], inv_form, in.pos2, in.pos1, n_, gdst));
       } else {
-        QDC_TRY(eng_rev_diag(stream_, ws_, state_, bwd_, gp[ii], in.pos2, in.pos1, n_, gdst));
+        PROF(gdst ? CAT_REV_DIAG : CAT_REV_CONST, 4,
+             eng_rev_diag(stream_, ws_, state_, bwd_, gp[ii], in.pos2, in.pos1, n_, gdst));
       }
       account(gdst ? 2 : 1, 2, 4);
     }

@@ -90,6 +90,10 @@ QDC_EXPORT const char* qdc_circuit_set_option(qdc_circuit* c, const char* key, l
     c->impl.opt_fuse_ = (int)value;
     return nullptr;
   }
+  if (strcmp(key, "profile") == 0) {
+    c->impl.prof_.on = value != 0;
+    return nullptr;
+  }
   return qdc_errf("Unknown option \"%s\".", key);
 }
 
@@ -101,6 +105,26 @@ QDC_EXPORT const char* qdc_circuit_last_stats(const qdc_circuit* c, qdc_stats* o
   out->kernel_launches = c->impl.stats_.kernel_launches;
   out->hbm_passes = c->impl.stats_.hbm_passes;
   out->algorithmic_bytes = c->impl.stats_.algorithmic_bytes;
+  return nullptr;
+}
+
+typedef struct {
+  uint64_t launches;
+  double ms;
+  uint64_t algorithmic_bytes;
+} qdc_profile_entry;
+
+QDC_EXPORT int qdc_profile_categories(void) { return CAT_COUNT; }
+
+QDC_EXPORT const char* qdc_profile_category_name(int cat) {
+  return (cat >= 0 && cat < CAT_COUNT) ? kProfCatNames[cat] : "";
+}
+
+QDC_EXPORT const char* qdc_circuit_last_profile(const qdc_circuit* c, int cat, qdc_profile_entry* out) {
+  if (cat < 0 || cat >= CAT_COUNT) return qdc_errf("Unknown profile category %d.", cat);
+  out->launches = c->impl.prof_.cats[cat].launches;
+  out->ms = c->impl.prof_.cats[cat].ms;
+  out->algorithmic_bytes = c->impl.prof_.cats[cat].alg_bytes;
   return nullptr;
 }
 

@@ -22,7 +22,7 @@ from typing import List, Sequence
 
 import numpy as np
 
-from .._ffi import Lib, QdcError, Stats, default_precision, get_lib
+from .._ffi import Lib, ProfileEntry, QdcError, Stats, default_precision, get_lib
 
 # enum Instruction, src/circuit.rs:53-68
 (CONST_Q2, VAR_Q2, CONST_Q2_NONU, VAR_Q2_NONU, CONST_Q2_DIAG, VAR_Q2_DIAG, CONST_Q1, CONST_Q1_NONU, VAR_Q1,
@@ -165,6 +165,18 @@ class Circuit:
         self._lib.call("qdc_circuit_last_stats", self._h, C.byref(s))
         return {"kernel_launches": s.kernel_launches, "hbm_passes": s.hbm_passes,
                 "algorithmic_bytes": s.algorithmic_bytes}
+
+
+    def last_profile(self) -> dict:
+        """Per-category device time of the last call (needs set_option("profile", 1))."""
+        out = {}
+        for cat in range(self._lib.cdll.qdc_profile_categories()):
+            e = ProfileEntry()
+            self._lib.call("qdc_circuit_last_profile", self._h, cat, C.byref(e))
+            if e.launches:
+                out[self._lib.cdll.qdc_profile_category_name(cat).decode()] = {
+                    "launches": e.launches, "ms": e.ms, "algorithmic_bytes": e.algorithmic_bytes}
+        return out
 
 
 def _variant(precision: str):

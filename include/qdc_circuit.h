@@ -85,7 +85,8 @@ const char* qdc_circuit_copy_state_to_host(qdc_circuit* c, qdc_complex* host_sta
 const char* qdc_circuit_state_device_ptr(qdc_circuit* c, void** device_ptr);
 /* Run on a caller-provided cudaStream_t (default: the legacy default stream). */
 const char* qdc_circuit_set_stream(qdc_circuit* c, void* cuda_stream);
-/* Tunables: "fuse" (0 = one pass per instruction, 1 = tiled multi-gate passes). */
+/* Tunables: "fuse" (0 = one pass per instruction, 1 = tiled multi-gate passes),
+ * "profile" (1 = time every launch group with CUDA events). */
 const char* qdc_circuit_set_option(qdc_circuit* c, const char* key, long value);
 /* Execution statistics of the last run/forward/backward call. */
 typedef struct {
@@ -94,6 +95,17 @@ typedef struct {
   uint64_t algorithmic_bytes; /* SURVEY.md section 8(d) accounting */
 } qdc_stats;
 const char* qdc_circuit_last_stats(const qdc_circuit* c, qdc_stats* out);
+
+/* Per-category device timing of the last call (CUDA events on the executing
+ * stream; enable with qdc_circuit_set_option(c, "profile", 1)). */
+typedef struct {
+  uint64_t launches;          /* timed launch groups in this category */
+  double ms;                  /* summed device time */
+  uint64_t algorithmic_bytes; /* SURVEY.md 8(d) bytes those launches account for */
+} qdc_profile_entry;
+int qdc_profile_categories(void);
+const char* qdc_profile_category_name(int category);
+const char* qdc_circuit_last_profile(const qdc_circuit* c, int category, qdc_profile_entry* out);
 
 /* Fused single reverse step on DEVICE buffers (the 4*S kernel):
  * fwd <- U^dagger fwd (or U^-1 fwd when non_unitary), grad (+)= sum bwd (x) fwd,
