@@ -48,6 +48,8 @@ _CIRCUIT_SIGNATURES = {
     "qdc_precision": (C.c_char_p, []),
     "qdc_abi_version": (C.c_int, []),
     "qdc_circuit_new": (_err, [C.POINTER(C.c_void_p), _sz]),
+    "qdc_circuit_new_sharded": (_err, [C.POINTER(C.c_void_p), _sz, C.c_int, C.c_int, C.c_void_p]),
+    "qdc_nccl_unique_id": (_err, [C.c_void_p]),
     "qdc_circuit_free": (_err, [C.c_void_p]),
     "qdc_circuit_set_state_from_host": (_err, [C.c_void_p, c_cplx_p, _sz]),
     "qdc_circuit_add": (_err, [C.c_void_p, C.c_int, _sz, _sz]),
@@ -66,6 +68,8 @@ _CIRCUIT_SIGNATURES = {
     "qdc_profile_categories": (C.c_int, []),
     "qdc_profile_category_name": (C.c_char_p, [C.c_int]),
     "qdc_circuit_last_profile": (_err, [C.c_void_p, C.c_int, C.c_void_p]),
+    "qdc_schedule": (_err, [_sz, _sz, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, _sz, C.c_int,
+                            C.c_void_p, _sz, C.POINTER(_sz)]),
     "qdc_reverse_step": (_err, [c_cplx_p, c_cplx_p, c_cplx_p, c_cplx_p, C.c_int, C.c_int, _sz, _sz, _sz]),
     "qdc_density_seed": (_err, [c_cplx_p, c_cplx_p, c_cplx_p, C.c_int, C.c_int, _sz, _sz, _sz]),
 }
@@ -148,6 +152,23 @@ def get_lib(precision: str) -> Lib:
     if precision not in _LIBS:
         _LIBS[precision] = Lib(precision)
     return _LIBS[precision]
+
+
+def schedule(instructions, n, n_loc=None, tile_bits=0, low_bits=0, max_tile_gates=0, all_densities=False,
+             precision="f32"):
+    """Run the C++ pass scheduler (pure host code) on `instructions`, a list of
+    (kind, pos2[, pos1]) tuples; returns the int64 plan encoding of qdc_schedule."""
+    lib = get_lib(precision)
+    kinds = np.array([i[0] for i in instructions], dtype=np.int32)
+    p2 = np.array([i[1] for i in instructions], dtype=np.uint64)
+    p1 = np.array([i[2] if len(i) > 2 else 0 for i in instructions], dtype=np.uint64)
+    cap = 64 + 16 * len(instructions) + 64 * len(instructions)
+    out = np.zeros(cap, dtype=np.int64)
+    n_out = C.c_size_t(0)
+    lib.call("qdc_schedule", n, n if n_loc is None else n_loc, tile_bits, low_bits, max_tile_gates,
+             kinds.ctypes.data, p2.ctypes.data, p1.ctypes.data, len(instructions), int(all_densities),
+             out.ctypes.data, cap, C.byref(n_out))
+    return out[:n_out.value].copy()
 
 
 def precision_of(dtype) -> str:

@@ -16,6 +16,8 @@
 #include <vector>
 
 #include "engine.cuh"
+#include "nccl_dyn.hpp"
+#include "scheduler.hpp"
 
 enum Kind {
   K_CONST_Q2 = 0, K_VAR_Q2, K_CONST_Q2_NONU, K_VAR_Q2_NONU, K_CONST_Q2_DIAG, K_VAR_Q2_DIAG,
@@ -125,16 +127,33 @@ struct Profiler {
     if (prof_.on) prof_.end(stream_, cat, pa_, (uint64_t)(alg_passes) * bytes()); \
   } while (0)
 
+// ---- half-shard pack / unpack for qubit-remap exchanges ------------------
+// dst[i] = src[i with bit `pos` forced to `val`]  (gather), or the inverse.
+template <typename V, bool GATHER>
+__global__ void __launch_bounds__(QDC_BLOCK)
+    k_half_copy(V* __restrict__ full, V* __restrict__ half, int pos, int val, uint64_t nhalf) {
+  const uint64_t stride = (uint64_t)gridDim.x * QDC_BLOCK;
+  for (uint64_t i = (uint64_t)blockIdx.x * QDC_BLOCK + threadIdx.x; i < nhalf; i += stride) {
+    const uint64_t j = ins0(i, pos) | ((uint64_t)val << pos);
+    if (GATHER) half[i] = full[j]; else full[j] = half[i];
+  }
+}
+
 class Circuit {
  public:
-  explicit Circuit(int n) : n_(n) {}
+  explicit Circuit(int n) : n_(n), n_loc_(n) {}
   ~Circuit() { release(); }
 
-  int n_;
+  int n_;       // logical qubits
+  int n_loc_;   // local physical positions (n_ - log2 world)
+  int rank_ = 0, world_ = 1;
+  qdc::ncclComm_t comm_ = nullptr;
   std::vector<Inst> insts_;
   cplx_t* state_ = nullptr;
   cplx_t* bwd_ = nullptr;
   cplx_t* initial_ = nullptr;  // nullptr <=> |0..0>
+  cplx_t* stage_a_ = nullptr;  // exchange staging (half shard each)
+  cplx_t* stage_b_ = nullptr;
   Workspace ws_;
   double* d_res_ = nullptr;  // device results: 32 doubles per slot
   size_t d_res_slots_ = 0;
@@ -142,24 +161,61 @@ class Circuit {
   cudaStream_t stream_ = 0;
   Stats stats_;
   int opt_fuse_ = 0;
+  int opt_tile_bits_ = 0;  // 0: default for the precision
+  int opt_low_bits_ = 0;
+  int opt_max_tile_gates_ = 24;
   Profiler prof_;
+  qdc::Plan plan_;            // plan of the last forward sweep (backward replays it reversed)
+  bool plan_all_dens_ = false;
+  std::vector<int> exec_p2_, exec_p1_;  // physical positions each instruction ran at
 
   void release() {
     if (state_) cudaFree(state_);
     if (bwd_) cudaFree(bwd_);
     if (initial_) cudaFree(initial_);
+    if (stage_a_) cudaFree(stage_a_);
+    if (stage_b_) cudaFree(stage_b_);
     if (d_res_) cudaFree(d_res_);
-    state_ = bwd_ = initial_ = nullptr;
+    state_ = bwd_ = initial_ = stage_a_ = stage_b_ = nullptr;
     d_res_ = nullptr;
     d_res_slots_ = 0;
     ws_release(ws_);
+    release_tiles();
+    if (comm_) {
+      qdc::nccl().CommDestroy(comm_);
+      comm_ = nullptr;
+    }
   }
 
-  size_t bytes() const { return sizeof(cplx_t) << n_; }
+  size_t bytes() const { return sizeof(cplx_t) << n_loc_; }
 
   const char* ensure_state() {
     if (!state_) QDC_CUDA(cudaMalloc((void**)&state_, bytes()));
     return nullptr;
+  }
+
+  // Sharding over `world` = 2^g ranks by the top g physical positions.
+  const char* shard(int rank, int world, const void* unique_id) {
+    if (world < 1 || (world & (world - 1)) != 0) return qdc_errf("world size must be a power of two.");
+    int g = 0;
+    while ((1 << g) < world) g++;
+    if (g >= n_) return qdc_errf("more ranks than amplitudes.");
+    if (state_) QDC_CUDA(cudaFree(state_));
+    state_ = nullptr;
+    if (bwd_) QDC_CUDA(cudaFree(bwd_));
+    bwd_ = nullptr;
+    rank_ = rank;
+    world_ = world;
+    n_loc_ = n_ - g;
+    if (world > 1) {
+      const char* e = qdc::nccl().load();
+      if (e) return qdc_errf("%s", e);
+      qdc::ncclUniqueId id;
+      memcpy(&id, unique_id, sizeof(id));
+      const int rc = qdc::nccl().CommInitRank(&comm_, world, id, rank);
+      if (rc != 0) return qdc_errf("ncclCommInitRank failed: %s", qdc::nccl().GetErrorString(rc));
+    }
+    return ensure_state();
   }
 
   const char* ensure_results(size_t slots) {
@@ -172,9 +228,10 @@ class Circuit {
     return nullptr;
   }
 
+  // In sharded mode `host` is this rank's shard (2^n_loc entries, identity qubit map).
   const char* set_state_from_host(const cplx_t* host, size_t len) {
     if (len == 0 || (len & (len - 1)) != 0) return qdc_errf("State size is not a power of 2.");
-    if (len != ((size_t)1 << n_))
+    if (len != ((size_t)1 << n_loc_))
       return qdc_errf("Size of the given state does not match the size of the tensor.");
     if (!initial_) QDC_CUDA(cudaMalloc((void**)&initial_, bytes()));
     QDC_CUDA(cudaMemcpy(initial_, host, bytes(), cudaMemcpyHostToDevice));
@@ -251,11 +308,175 @@ class Circuit {
   const char* reset_state() {
     QDC_TRY(ensure_state());
     if (initial_) {
-      QDC_TRY(eng_copy(stream_, initial_, state_, n_));  // data_transfer, src/circuit.rs:174,225
+      QDC_TRY(eng_copy(stream_, initial_, state_, n_loc_));  // data_transfer, src/circuit.rs:174,225
     } else {
-      QDC_TRY(eng_set_standard(stream_, state_, n_));
+      QDC_CUDA(cudaMemsetAsync(state_, 0, bytes(), stream_));
+      if (rank_ == 0) {
+        k_set_one<<<1, 1, 0, stream_>>>(state_);
+        QDC_CUDA(cudaGetLastError());
+      }
       account(1, 0, 0);
     }
+    return nullptr;
+  }
+
+  // ------------------------------------------------------------ planning
+  static int sched_class(int k) {
+    if (kind_is_q1(k)) return 0;
+    if (kind_is_q2dense(k)) return 1;
+    if (kind_is_diag(k)) return 2;
+    return kind_is_q1_dens(k) ? 3 : 4;
+  }
+
+  // One plan serves forward and backward; the backward kernel keeps state AND
+  // adjoint tiles resident, so T is sized for it (2 * 2^T * sizeof(complex) = 64 KiB).
+  int default_tile_bits() const {
+#ifdef QDC_F64
+    return 11;
+#else
+    return 12;
+#endif
+  }
+  int min_tile_bits() const { return QDC_LV + 10; }
+  int default_low_bits() const {
+#ifdef QDC_F64
+    return 3;
+#else
+    return 4;
+#endif
+  }
+
+  qdc::SchedOptions sched_options() const {
+    qdc::SchedOptions so;
+    so.n = n_;
+    so.n_loc = n_loc_;
+    if (opt_fuse_) {
+      so.tile_bits = opt_tile_bits_ ? opt_tile_bits_ : default_tile_bits();
+      so.low_bits = opt_low_bits_ ? opt_low_bits_ : default_low_bits();
+      so.max_tile_gates = opt_max_tile_gates_;
+      if (so.tile_bits > n_loc_) so.tile_bits = n_loc_;
+      if (so.tile_bits < min_tile_bits() || so.low_bits > so.tile_bits - 2) so.tile_bits = 0;  // too small to tile
+    }
+    return so;
+  }
+
+  void build_plan(bool all_dens) {
+    std::vector<qdc::SchedInst> si(insts_.size());
+    for (size_t i = 0; i < insts_.size(); i++) {
+      const int k = insts_[i].kind;
+      si[i].kind_class = sched_class(k);
+      si[i].q2 = insts_[i].pos2;
+      si[i].q1 = insts_[i].pos1;
+      si[i].skip = kind_is_dens(k) && !all_dens && !kind_is_diff_dens(k);
+    }
+    qdc::Scheduler sch(si, sched_options());
+    plan_ = sch.run();
+    plan_all_dens_ = all_dens;
+    exec_p2_.assign(insts_.size(), -1);
+    exec_p1_.assign(insts_.size(), -1);
+    auto note = [&](const qdc::Step& st) {
+      if (st.inst >= 0) {
+        exec_p2_[st.inst] = st.p2;
+        exec_p1_[st.inst] = st.p1;
+      }
+    };
+    for (const qdc::Step& st : plan_.steps) note(st);
+    for (const qdc::Step& st : plan_.tile_steps) note(st);
+  }
+
+  // ------------------------------------------------- diagonal on global bits
+  // Effective local form of a diagonal gate some of whose positions are rank
+  // bits: returns the 4 entries to feed the elementwise kernel selected by
+  // (sel2, sel1) (both local).  j' = 2 bit(sel2) + bit(sel1) takes only the
+  // values 0 and 3 when sel2 == sel1.
+  void effective_diag(const cplx_t* d, int p2, int p1, cplx_t (&e)[4], int& sel2, int& sel1) const {
+    const bool g2 = p2 >= n_loc_, g1 = p1 >= n_loc_;
+    const int c2 = g2 ? (rank_ >> (p2 - n_loc_)) & 1 : 0, c1 = g1 ? (rank_ >> (p1 - n_loc_)) & 1 : 0;
+    for (int j = 0; j < 4; j++) e[j] = d[j];
+    sel2 = p2;
+    sel1 = p1;
+    if (g2 && g1) {
+      e[0] = e[3] = d[2 * c2 + c1];
+      sel2 = sel1 = 0;
+    } else if (g2) {
+      e[0] = d[2 * c2 + 0];
+      e[3] = d[2 * c2 + 1];
+      sel2 = sel1 = p1;
+    } else if (g1) {
+      e[0] = d[0 + c1];
+      e[3] = d[2 + c1];
+      sel2 = sel1 = p2;
+    }
+  }
+
+  // kernel-order diagonal gradient (8 doubles) -> reference order on this rank
+  void scatter_diag_grad(const double* h, int p2, int p1, zc (&out)[4]) const {
+    const bool g2 = p2 >= n_loc_, g1 = p1 >= n_loc_;
+    const int c2 = g2 ? (rank_ >> (p2 - n_loc_)) & 1 : 0, c1 = g1 ? (rank_ >> (p1 - n_loc_)) & 1 : 0;
+    for (int j = 0; j < 4; j++) out[j] = zc(0, 0);
+    if (!g2 && !g1) {
+      for (int j = 0; j < 4; j++) out[j] = zc(h[2 * j], h[2 * j + 1]);
+    } else if (g2 && g1) {
+      out[2 * c2 + c1] = zc(h[0] + h[6], h[1] + h[7]);
+    } else if (g2) {
+      out[2 * c2 + 0] = zc(h[0], h[1]);
+      out[2 * c2 + 1] = zc(h[6], h[7]);
+    } else {
+      out[0 + c1] = zc(h[0], h[1]);
+      out[2 + c1] = zc(h[6], h[7]);
+    }
+  }
+
+  // ---------------------------------------------------------- exchanges
+  const char* ensure_staging() {
+    const size_t half = bytes() / 2;
+    if (!stage_a_) QDC_CUDA(cudaMalloc((void**)&stage_a_, half));
+    if (!stage_b_) QDC_CUDA(cudaMalloc((void**)&stage_b_, half));
+    return nullptr;
+  }
+
+  template <bool GATHER>
+  const char* half_copy(cplx_t* full, cplx_t* half, int pos, int val) {
+    DeviceInfo di;
+    QDC_TRY(qdc_device_info(&di));
+    if (pos >= QDC_LV) {
+      const uint64_t nhalf = 1ull << (n_loc_ - 1 - QDC_LV);
+      const int grid = pick_grid(nhalf, 1, 8, di.sm_count);
+      k_half_copy<vec_t, GATHER><<<grid, QDC_BLOCK, 0, stream_>>>((vec_t*)full, (vec_t*)half, pos - QDC_LV, val,
+                                                                  nhalf);
+    } else {
+      const uint64_t nhalf = 1ull << (n_loc_ - 1);
+      const int grid = pick_grid(nhalf, 1, 8, di.sm_count);
+      k_half_copy<cplx_t, GATHER><<<grid, QDC_BLOCK, 0, stream_>>>(full, half, pos, val, nhalf);
+    }
+    QDC_CUDA(cudaGetLastError());
+    return nullptr;
+  }
+
+  // Swap global bit `gbit` with local position `lpos` of buffer `buf`:
+  // new[lpos=b, rank bit=c] = old[lpos=c, rank bit=b].  This rank keeps its
+  // half lpos == c and trades its half lpos == 1-c for the partner's half
+  // lpos == c (the partner sees the mirror image).
+  const char* exchange(cplx_t* buf, int gbit, int lpos) {
+    QDC_TRY(ensure_staging());
+    const int c = (rank_ >> gbit) & 1, partner = rank_ ^ (1 << gbit);
+    const size_t half_bytes = bytes() / 2;
+    const bool top = lpos == n_loc_ - 1;
+    cplx_t* out_half = top ? buf + ((size_t)(1 - c) << (n_loc_ - 1)) : stage_a_;
+    if (!top) QDC_TRY((half_copy<true>(buf, stage_a_, lpos, 1 - c)));
+    qdc::NcclApi& api = qdc::nccl();
+    int rc = api.GroupStart();
+    if (rc == 0) rc = api.Send(out_half, half_bytes, qdc::kNcclChar, partner, comm_, stream_);
+    if (rc == 0) rc = api.Recv(stage_b_, half_bytes, qdc::kNcclChar, partner, comm_, stream_);
+    const int rc2 = api.GroupEnd();
+    if (rc == 0) rc = rc2;
+    if (rc != 0) return qdc_errf("NCCL exchange failed: %s", api.GetErrorString(rc));
+    if (top) {
+      QDC_CUDA(cudaMemcpyAsync(out_half, stage_b_, half_bytes, cudaMemcpyDeviceToDevice, stream_));
+    } else {
+      QDC_TRY((half_copy<false>(buf, stage_b_, lpos, 1 - c)));
+    }
+    account(top ? 1 : 2, 1, 0);
     return nullptr;
   }
 
@@ -271,6 +492,7 @@ class Circuit {
     if (cap < need) return qdc_errf("Output buffer too small: %zu < %zu.", cap, need);
     const size_t nslots = count(all_dens ? 3 : 4);
     QDC_TRY(ensure_results(nslots));
+    build_plan(all_dens);
     QDC_TRY(reset_state());
     QDC_TRY(run_forward(gp, all_dens));
     // single read-back of every density
@@ -281,22 +503,23 @@ class Circuit {
     QDC_CUDA(cudaStreamSynchronize(stream_));
     if (prof_.on) prof_.collect();
     size_t slot = 0, o = 0;
-    for (const Inst& in : insts_) {
+    for (size_t i = 0; i < insts_.size(); i++) {
+      const Inst& in = insts_[i];
       if (!kind_is_dens(in.kind)) continue;
       if (!all_dens && !kind_is_diff_dens(in.kind)) continue;
       const double* h = &h_res_[slot * 32];
       if (kind_is_q1_dens(in.kind)) {
-        for (int i = 0; i < 4; i++) {
-          out[o + i].x = (real_t)h[2 * i];
-          out[o + i].y = (real_t)h[2 * i + 1];
+        for (int j = 0; j < 4; j++) {
+          out[o + j].x = (real_t)h[2 * j];
+          out[o + j].y = (real_t)h[2 * j + 1];
         }
         o += 4;
       } else {
         zc m[16];
-        unpermute_q2(h, in.pos2 < in.pos1, m);
-        for (int i = 0; i < 16; i++) {
-          out[o + i].x = (real_t)m[i].real();
-          out[o + i].y = (real_t)m[i].imag();
+        unpermute_q2(h, exec_p2_[i] < exec_p1_[i], m);
+        for (int j = 0; j < 16; j++) {
+          out[o + j].x = (real_t)m[j].real();
+          out[o + j].y = (real_t)m[j].imag();
         }
         o += 16;
       }
@@ -306,30 +529,53 @@ class Circuit {
     return nullptr;
   }
 
+  const char* fwd_gate_step(const qdc::Step& st, const std::vector<const cplx_t*>& gp) {
+    const int k = insts_[st.inst].kind;
+    if (kind_is_q1(k)) {
+      PROF(CAT_FWD_Q1, 2, eng_q1gate(stream_, ws_, state_, gp[st.inst], FORM_PLAIN, st.p2, n_loc_));
+    } else if (kind_is_q2dense(k)) {
+      PROF(CAT_FWD_Q2, 2, eng_q2gate(stream_, ws_, state_, gp[st.inst], FORM_PLAIN, st.p2, st.p1, n_loc_));
+    } else {
+      cplx_t e[4];
+      int s2, s1;
+      effective_diag(gp[st.inst], st.p2, st.p1, e, s2, s1);
+      PROF(CAT_FWD_DIAG, 2, eng_q2diag(stream_, ws_, state_, e, false, s2, s1, n_loc_));
+    }
+    account(1, 1, 2);
+    return nullptr;
+  }
+
   const char* run_forward(const std::vector<const cplx_t*>& gp, bool all_dens) {
-    size_t slot = 0;
-    for (size_t i = 0; i < insts_.size(); i++) {
-      const Inst& in = insts_[i];
-      const int k = in.kind;
-      if (kind_is_q1(k)) {
-        PROF(CAT_FWD_Q1, 2, eng_q1gate(stream_, ws_, state_, gp[i], FORM_PLAIN, in.pos2, n_));
-        account(1, 1, 2);
-      } else if (kind_is_q2dense(k)) {
-        PROF(CAT_FWD_Q2, 2, eng_q2gate(stream_, ws_, state_, gp[i], FORM_PLAIN, in.pos2, in.pos1, n_));
-        account(1, 1, 2);
-      } else if (kind_is_diag(k)) {
-        PROF(CAT_FWD_DIAG, 2, eng_q2diag(stream_, ws_, state_, gp[i], false, in.pos2, in.pos1, n_));
-        account(1, 1, 2);
-      } else {
-        if (!all_dens && !kind_is_diff_dens(k)) continue;
-        double* dst = d_res_ + slot * 32;
-        if (kind_is_q1_dens(k)) {
-          PROF(CAT_DENSITY, 1, eng_dens_q1(stream_, ws_, state_, in.pos2, n_, dst));
-        } else {
-          PROF(CAT_DENSITY, 1, eng_dens_q2(stream_, ws_, state_, in.pos2, in.pos1, n_, dst));
+    // output slot of every evaluated density, in program order
+    std::vector<long> dslot(insts_.size(), -1);
+    {
+      long s = 0;
+      for (size_t i = 0; i < insts_.size(); i++) {
+        const int k = insts_[i].kind;
+        if (kind_is_dens(k) && (all_dens || kind_is_diff_dens(k))) dslot[i] = s++;
+      }
+    }
+    for (const qdc::Step& st : plan_.steps) {
+      switch (st.type) {
+        case qdc::ST_GATE:
+          QDC_TRY(fwd_gate_step(st, gp));
+          break;
+        case qdc::ST_TILE:
+          QDC_TRY(run_tile_forward(st, gp));
+          break;
+        case qdc::ST_SWAP:
+          PROF(CAT_EXCHANGE, 0, exchange(state_, st.gbit, st.lpos));
+          break;
+        case qdc::ST_DENS: {
+          double* dst = d_res_ + (size_t)dslot[st.inst] * 32;
+          if (st.p1 < 0) {
+            PROF(CAT_DENSITY, 1, eng_dens_q1(stream_, ws_, state_, st.p2, n_loc_, dst));
+          } else {
+            PROF(CAT_DENSITY, 1, eng_dens_q2(stream_, ws_, state_, st.p2, st.p1, n_loc_, dst));
+          }
+          account(2, 1, 1);
+          break;
         }
-        account(2, 1, 1);
-        slot++;
       }
     }
     return nullptr;
@@ -339,7 +585,7 @@ class Circuit {
   const char* backward(const GateList& dg, const GateList& cg, const GateList& vg, cplx_t* out, size_t cap,
                        size_t* out_len) {
     if (insts_.empty()) return qdc_errf("The circuit is empty.");
-    if (!state_) return qdc_errf("backward() called before forward().");
+    if (!state_ || plan_.steps.empty()) return qdc_errf("backward() called before forward().");
     stats_ = Stats();
     prof_.reset();
     std::vector<const cplx_t*> gp;
@@ -388,12 +634,20 @@ class Circuit {
       const double* h = &h_res_[(size_t)vslot[i] * 32];
       if (kind_is_q2dense(in.kind)) {
         zc m[16];
-        unpermute_q2(h, in.pos2 < in.pos1, m);
+        unpermute_q2(h, exec_p2_[i] < exec_p1_[i], m);
         for (int j = 0; j < 16; j++) {
           out[o + j].x = (real_t)m[j].real();
           out[o + j].y = (real_t)m[j].imag();
         }
         o += 16;
+      } else if (kind_is_diag(in.kind)) {
+        zc m[4];
+        scatter_diag_grad(h, exec_p2_[i], exec_p1_[i], m);
+        for (int j = 0; j < 4; j++) {
+          out[o + j].x = (real_t)m[j].real();
+          out[o + j].y = (real_t)m[j].imag();
+        }
+        o += 4;
       } else {
         for (int j = 0; j < 4; j++) {
           out[o + j].x = (real_t)h[2 * j];
@@ -406,51 +660,82 @@ class Circuit {
     return nullptr;
   }
 
+  const char* bwd_gate_step(const qdc::Step& st, const std::vector<const cplx_t*>& gp,
+                            const std::vector<long>& vslot, bool live) {
+    const int ii = st.inst;
+    const int k = insts_[ii].kind;
+    const int inv_form = kind_is_nonu(k) ? FORM_INV : FORM_CONJ_TR;
+    double* gdst = (vslot[ii] >= 0) ? d_res_ + (size_t)vslot[ii] * 32 : nullptr;
+    cplx_t e[4];
+    int s2 = st.p2, s1 = st.p1;
+    if (kind_is_diag(k)) effective_diag(gp[ii], st.p2, st.p1, e, s2, s1);
+    if (!live) {
+      // no adjoint yet: un-compute only; variable gates keep their zero gradient
+      if (kind_is_q1(k)) {
+        PROF(CAT_UNCOMPUTE, 2, eng_q1gate(stream_, ws_, state_, gp[ii], inv_form, st.p2, n_loc_));
+      } else if (kind_is_q2dense(k)) {
+        PROF(CAT_UNCOMPUTE, 2, eng_q2gate(stream_, ws_, state_, gp[ii], inv_form, st.p2, st.p1, n_loc_));
+      } else {
+        PROF(CAT_UNCOMPUTE, 2, eng_q2diag(stream_, ws_, state_, e, true, s2, s1, n_loc_));
+      }
+      account(1, 1, 2);
+      return nullptr;
+    }
+    if (kind_is_q1(k)) {
+      PROF(gdst ? CAT_REV_Q1 : CAT_REV_CONST, 4,
+           eng_rev_q1(stream_, ws_, state_, bwd_, gp[ii], inv_form, st.p2, n_loc_, gdst));
+    } else if (kind_is_q2dense(k)) {
+      PROF(gdst ? CAT_REV_Q2 : CAT_REV_CONST, 4,
+           eng_rev_q2(stream_, ws_, state_, bwd_, gp[ii], inv_form, st.p2, st.p1, n_loc_, gdst));
+    } else {
+      PROF(gdst ? CAT_REV_DIAG : CAT_REV_CONST, 4,
+           eng_rev_diag(stream_, ws_, state_, bwd_, e, s2, s1, n_loc_, gdst));
+    }
+    account(gdst ? 2 : 1, 2, 4);
+    return nullptr;
+  }
+
   const char* run_backward(const std::vector<const cplx_t*>& gp, const std::vector<const cplx_t*>& dp,
                            const std::vector<long>& vslot) {
     bool live = false;  // is there an adjoint yet? (bwd_option, src/circuit.rs:276)
-    for (size_t ii = insts_.size(); ii-- > 0;) {
-      const Inst& in = insts_[ii];
-      const int k = in.kind;
-      if (k == K_Q1_DENS || k == K_Q2_DENS) continue;
-      if (k == K_DIFF_Q1_DENS) {
-        PROF(CAT_SEED, live ? 3 : 2, eng_seed_q1(stream_, ws_, state_, bwd_, dp[ii], in.pos2, n_, live));
-        account(1, 1, live ? 3 : 2);
-        live = true;
-        continue;
-      }
-      if (k == K_DIFF_Q2_DENS) {
-        PROF(CAT_SEED, live ? 3 : 2, eng_seed_q2(stream_, ws_, state_, bwd_, dp[ii], in.pos2, in.pos1, n_, live));
-        account(1, 1, live ? 3 : 2);
-        live = true;
-        continue;
-      }
-      const int inv_form = kind_is_nonu(k) ? FORM_INV : FORM_CONJ_TR;
-      double* gdst = (vslot[ii] >= 0) ? d_res_ + (size_t)vslot[ii] * 32 : nullptr;
-      if (!live) {
-        // no adjoint yet: un-compute only; variable gates keep their zero gradient
-        if (kind_is_q1(k)) {
-          PROF(CAT_UNCOMPUTE, 2, eng_q1gate(stream_, ws_, state_, gp[ii], inv_form, in.pos2, n_));
-        } else if (kind_is_q2dense(k)) {
-          PROF(CAT_UNCOMPUTE, 2, eng_q2gate(stream_, ws_, state_, gp[ii], inv_form, in.pos2, in.pos1, n_));
-        } else {
-          PROF(CAT_UNCOMPUTE, 2, eng_q2diag(stream_, ws_, state_, gp[ii], true, in.pos2, in.pos1, n_));
+    for (size_t si = plan_.steps.size(); si-- > 0;) {
+      const qdc::Step& st = plan_.steps[si];
+      switch (st.type) {
+        case qdc::ST_DENS: {
+          const int k = insts_[st.inst].kind;
+          if (!kind_is_diff_dens(k)) break;
+          if (st.p1 < 0) {
+            PROF(CAT_SEED, live ? 3 : 2,
+                 eng_seed_q1(stream_, ws_, state_, bwd_, dp[st.inst], st.p2, n_loc_, live));
+          } else {
+            PROF(CAT_SEED, live ? 3 : 2,
+                 eng_seed_q2(stream_, ws_, state_, bwd_, dp[st.inst], st.p2, st.p1, n_loc_, live));
+          }
+          account(1, 1, live ? 3 : 2);
+          live = true;
+          break;
         }
-        account(1, 1, 2);
-        continue;
+        case qdc::ST_GATE:
+          QDC_TRY(bwd_gate_step(st, gp, vslot, live));
+          break;
+        case qdc::ST_TILE:
+          QDC_TRY(run_tile_backward(st, gp, vslot, live));
+          break;
+        case qdc::ST_SWAP:
+          PROF(CAT_EXCHANGE, 0, exchange(state_, st.gbit, st.lpos));
+          if (live) PROF(CAT_EXCHANGE, 0, exchange(bwd_, st.gbit, st.lpos));
+          break;
       }
-      if (kind_is_q1(k)) {
-        PROF(gdst ? CAT_REV_Q1 : CAT_REV_CONST, 4,
-             eng_rev_q1(stream_, ws_, state_, bwd_, gp[ii], inv_form, in.pos2, n_, gdst));
-      } else if (kind_is_q2dense(k)) {
-        PROF(gdst ? CAT_REV_Q2 : CAT_REV_CONST, 4,
-             eng_rev_q2(stream_, ws_, state_, bwd_, gp[ii], inv_form, in.pos2, in.pos1, n_, gdst));
-      } else {
-        PROF(gdst ? CAT_REV_DIAG : CAT_REV_CONST, 4,
-             eng_rev_diag(stream_, ws_, state_, bwd_, gp[ii], in.pos2, in.pos1, n_, gdst));
-      }
-      account(gdst ? 2 : 1, 2, 4);
     }
     return nullptr;
   }
+
+  // ------------------------------------------------------- tiled passes
+  // (tile_kernels.cuh)
+  const char* run_tile_forward(const qdc::Step& t, const std::vector<const cplx_t*>& gp);
+  const char* run_tile_backward(const qdc::Step& t, const std::vector<const cplx_t*>& gp,
+                                const std::vector<long>& vslot, bool live);
+  void release_tiles();
+  double* tile_partials_ = nullptr;
+  size_t tile_partials_cap_ = 0;
 };

@@ -3,7 +3,7 @@
 // Exports: the 18 legacy symbols (include/qdc_primitives.h) and the circuit
 // ABI (include/qdc_circuit.h).  Everything else has hidden visibility.
 #include "primitives_abi.cuh"
-#include "circuit.cuh"
+#include "tile_kernels.cuh"
 
 struct qdc_circuit {
   Circuit impl;
@@ -18,7 +18,7 @@ QDC_EXPORT const char* qdc_precision(void) {
 #endif
 }
 
-QDC_EXPORT int qdc_abi_version(void) { return 1; }
+QDC_EXPORT int qdc_abi_version(void) { return 2; }
 
 QDC_EXPORT const char* qdc_circuit_new(qdc_circuit** out, size_t qubits_number) {
   if (qubits_number < 1 || qubits_number > 40) return qdc_errf("qubits_number out of range.");
@@ -29,6 +29,31 @@ QDC_EXPORT const char* qdc_circuit_new(qdc_circuit** out, size_t qubits_number) 
     return e;
   }
   *out = c;
+  return nullptr;
+}
+
+// Sharded construction: rank r of world = 2^g owns the amplitudes whose top g
+// index bits equal r; the NCCL communicator is created from `nccl_unique_id`.
+QDC_EXPORT const char* qdc_circuit_new_sharded(qdc_circuit** out, size_t qubits_number, int rank, int world,
+                                               const void* nccl_unique_id) {
+  if (qubits_number < 1 || qubits_number > 48) return qdc_errf("qubits_number out of range.");
+  qdc_circuit* c = new qdc_circuit((int)qubits_number);
+  const char* e = c->impl.shard(rank, world, nccl_unique_id);
+  if (e) {
+    delete c;
+    return e;
+  }
+  *out = c;
+  return nullptr;
+}
+
+QDC_EXPORT const char* qdc_nccl_unique_id(void* out128) {
+  const char* e = qdc::nccl().load();
+  if (e) return qdc_errf("%s", e);
+  qdc::ncclUniqueId id;
+  const int rc = qdc::nccl().GetUniqueId(&id);
+  if (rc != 0) return qdc_errf("ncclGetUniqueId failed: %s", qdc::nccl().GetErrorString(rc));
+  memcpy(out128, &id, sizeof(id));
   return nullptr;
 }
 
@@ -67,6 +92,8 @@ QDC_EXPORT const char* qdc_circuit_backward(qdc_circuit* c, const cplx_t* dgrads
                           GateList{vgates, vlens, nv}, out, cap, out_len);
 }
 
+// Working state of this rank: 2^(n - log2 world) entries in the CURRENT
+// physical layout (identity qubit map before forward and after backward).
 QDC_EXPORT const char* qdc_circuit_copy_state_to_host(qdc_circuit* c, cplx_t* host_state) {
   QDC_TRY(c->impl.ensure_state());
   QDC_CUDA(cudaStreamSynchronize(c->impl.stream_));
@@ -86,15 +113,15 @@ QDC_EXPORT const char* qdc_circuit_set_stream(qdc_circuit* c, void* cuda_stream)
 }
 
 QDC_EXPORT const char* qdc_circuit_set_option(qdc_circuit* c, const char* key, long value) {
-  if (strcmp(key, "fuse") == 0) {
-    c->impl.opt_fuse_ = (int)value;
-    return nullptr;
-  }
-  if (strcmp(key, "profile") == 0) {
-    c->impl.prof_.on = value != 0;
-    return nullptr;
-  }
-  return qdc_errf("Unknown option \"%s\".", key);
+  if (strcmp(key, "fuse") == 0) c->impl.opt_fuse_ = (int)value;
+  else if (strcmp(key, "profile") == 0) c->impl.prof_.on = value != 0;
+  else if (strcmp(key, "tile_bits") == 0) c->impl.opt_tile_bits_ = (int)value;
+  else if (strcmp(key, "low_bits") == 0) c->impl.opt_low_bits_ = (int)value;
+  else if (strcmp(key, "max_tile_gates") == 0) {
+    if (value < 1 || value > QDC_TILE_MAXG_B) return qdc_errf("max_tile_gates must be in 1..%d.", QDC_TILE_MAXG_B);
+    c->impl.opt_max_tile_gates_ = (int)value;
+  } else return qdc_errf("Unknown option \"%s\".", key);
+  return nullptr;
 }
 
 typedef struct {
@@ -125,6 +152,54 @@ QDC_EXPORT const char* qdc_circuit_last_profile(const qdc_circuit* c, int cat, q
   out->launches = c->impl.prof_.cats[cat].launches;
   out->ms = c->impl.prof_.cats[cat].ms;
   out->algorithmic_bytes = c->impl.prof_.cats[cat].alg_bytes;
+  return nullptr;
+}
+
+// ---- scheduler as a pure function (no device needed) ---------------------
+// Encoding of the plan, all int64, one record per step:
+//   [type, inst, p2, p1, gbit, lpos, count, nbits] then, for TILE steps,
+//   count x [inst, p2, p1] followed by nbits x [physical bit].
+// After the last step: [-1, n, final_map[0..n-1]].
+QDC_EXPORT const char* qdc_schedule(size_t n, size_t n_loc, int tile_bits, int low_bits, int max_tile_gates,
+                                    const int* kinds, const size_t* pos2, const size_t* pos1, size_t count,
+                                    int all_densities, int64_t* out, size_t cap, size_t* out_len) {
+  std::vector<qdc::SchedInst> si(count);
+  for (size_t i = 0; i < count; i++) {
+    const int k = kinds[i];
+    if (k < 0 || k > K_DIFF_Q1_DENS) return qdc_errf("Unknown instruction kind %d.", k);
+    si[i].kind_class = Circuit::sched_class(k);
+    si[i].q2 = (int)pos2[i];
+    si[i].q1 = (kind_is_q1(k) || kind_is_q1_dens(k)) ? -1 : (int)pos1[i];
+    si[i].skip = kind_is_dens(k) && !all_densities && !kind_is_diff_dens(k);
+  }
+  qdc::SchedOptions so;
+  so.n = (int)n;
+  so.n_loc = (int)n_loc;
+  so.tile_bits = tile_bits;
+  so.low_bits = low_bits;
+  if (max_tile_gates > 0) so.max_tile_gates = max_tile_gates;
+  qdc::Scheduler sch(si, so);
+  const qdc::Plan plan = sch.run();
+  std::vector<int64_t> enc;
+  for (const qdc::Step& st : plan.steps) {
+    const int64_t rec[8] = {st.type, st.inst, st.p2, st.p1, st.gbit, st.lpos, st.count, st.tb_count};
+    enc.insert(enc.end(), rec, rec + 8);
+    if (st.type == qdc::ST_TILE) {
+      for (int k = 0; k < st.count; k++) {
+        const qdc::Step& g = plan.tile_steps[st.first + k];
+        enc.push_back(g.inst);
+        enc.push_back(g.p2);
+        enc.push_back(g.p1);
+      }
+      for (int k = 0; k < st.tb_count; k++) enc.push_back(plan.tile_bits[st.tb_first + k]);
+    }
+  }
+  enc.push_back(-1);
+  enc.push_back((int64_t)n);
+  for (int q = 0; q < (int)n; q++) enc.push_back(plan.final_map[q]);
+  *out_len = enc.size();
+  if (enc.size() > cap) return qdc_errf("plan buffer too small: %zu < %zu.", cap, enc.size());
+  memcpy(out, enc.data(), enc.size() * sizeof(int64_t));
   return nullptr;
 }
 

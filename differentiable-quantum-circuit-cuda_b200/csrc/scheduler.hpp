@@ -1,0 +1,263 @@
+// Pass scheduler (pure host C++, no CUDA): turns the instruction list of a
+// circuit (/root/reference/src/circuit.rs:53-68) into a PLAN -- the sequence of
+// passes the executor runs.  The reference has no counterpart: it issues one
+// kernel per instruction in program order (src/circuit.rs:175, 226, 278).
+//
+// What the plan may change, and why it is exact:
+//  * Gates acting on disjoint qubits commute as operators, and the reverse-mode
+//    quantities of a gate (pre-gate state, post-gate adjoint) are invariant
+//    under moving a disjoint gate across it (DESIGN.md "Reordering").  So gates
+//    may be re-ordered within the dependency DAG defined by shared qubits.
+//  * Density instructions are full barriers (a Diff density must see exactly
+//    the gates that precede it in program order, otherwise the gradients of
+//    non-unitary directions change).
+//
+// Sharding: with 2^g ranks the top g PHYSICAL bit positions are the rank
+// index ("global").  A logical->physical qubit map is maintained; dense gates
+// and densities need all their qubits on local positions, diagonal gates do
+// not.  When nothing more can run, global qubits are swapped with the local
+// qubits whose next use is farthest away (one half-shard exchange per swapped
+// pair), which for 1-D brickwork yields the light-cone ("diamond") schedule.
+//
+// Tiling: consecutive runnable local gates are grouped into TILE passes: a set
+// of at most T physical bit positions (always containing the low L bits, for
+// coalescing) such that every gate of the pass acts inside the set; the
+// executor then streams the state once for the whole group.
+#pragma once
+#include <algorithm>
+#include <cstdint>
+#include <vector>
+
+namespace qdc {
+
+enum StepType : int { ST_GATE = 0, ST_DENS = 1, ST_SWAP = 2, ST_TILE = 3 };
+
+struct Step {
+  int type = ST_GATE;
+  int inst = -1;          // GATE / DENS: instruction index
+  int p2 = -1, p1 = -1;   // GATE / DENS: physical positions at execution time (p1 = -1: one-qubit)
+  int gbit = -1, lpos = -1;  // SWAP: global bit index (physical position n_loc + gbit) <-> local position
+  int first = 0, count = 0;  // TILE: range in Plan::tile_steps
+  int tb_first = 0, tb_count = 0;  // TILE: range in Plan::tile_bits (sorted physical positions)
+};
+
+struct Plan {
+  std::vector<Step> steps;
+  std::vector<Step> tile_steps;   // GATE steps belonging to TILE passes
+  std::vector<int> tile_bits;
+  std::vector<int> final_map;     // logical qubit -> physical position after the plan
+};
+
+struct SchedInst {
+  int kind_class;  // 0: dense q1, 1: dense q2, 2: diagonal q2, 3: density q1, 4: density q2
+  int q2, q1;      // logical qubits (q1 = -1 for one-qubit instructions)
+  bool skip;       // densities that this sweep does not evaluate
+};
+
+struct SchedOptions {
+  int n = 0;         // total (logical) qubits
+  int n_loc = 0;     // local physical positions per rank (n - g)
+  int tile_bits = 0; // T: 0 disables tiling
+  int low_bits = 0;  // L: low physical positions forced into every tile
+  int min_tile_gates = 2;  // a tile pass must hold at least this many gates to beat streaming
+  int max_tile_gates = 24; // capacity of the backward tile kernel's parameter block
+};
+
+class Scheduler {
+ public:
+  Scheduler(const std::vector<SchedInst>& insts, const SchedOptions& opt) : in_(insts), o_(opt) {}
+
+  Plan run() {
+    Plan plan;
+    const int N = (int)in_.size();
+    done_.assign(N, false);
+    map_.resize(o_.n);
+    for (int q = 0; q < o_.n; q++) map_[q] = q;
+    int remaining = 0;
+    for (int i = 0; i < N; i++) {
+      if (in_[i].skip) done_[i] = true; else remaining++;
+    }
+    while (remaining > 0) {
+      std::vector<Step> ready;
+      collect_ready(ready);
+      if (!ready.empty()) {
+        remaining -= (int)ready.size();
+        emit(plan, ready);
+        continue;
+      }
+      // nothing runnable: bring needed global qubits onto local positions
+      if (!remap(plan)) break;  // cannot happen for valid input; avoids an endless loop
+    }
+    plan.final_map = map_;
+    return plan;
+  }
+
+ private:
+  const std::vector<SchedInst>& in_;
+  SchedOptions o_;
+  std::vector<bool> done_;
+  std::vector<int> map_;  // logical -> physical
+
+  bool is_dens(const SchedInst& s) const { return s.kind_class >= 3; }
+  bool local(int q) const { return map_[q] < o_.n_loc; }
+
+  // One sweep in program order: every instruction whose predecessors (on its
+  // qubits) are done and whose placement allows it to run now.
+  void collect_ready(std::vector<Step>& ready) {
+    const int N = (int)in_.size();
+    std::vector<bool> blocked(o_.n, false);
+    bool any_blocked = false;
+    for (int i = 0; i < N; i++) {
+      if (done_[i]) continue;
+      const SchedInst& s = in_[i];
+      if (is_dens(s)) {
+        // barrier: runs only if everything before it is done
+        if (any_blocked) break;
+        const bool ok = local(s.q2) && (s.q1 < 0 || local(s.q1));
+        if (!ok) break;
+        ready.push_back(make_step(i, ST_DENS));
+        done_[i] = true;
+        continue;
+      }
+      const bool dep = blocked[s.q2] || (s.q1 >= 0 && blocked[s.q1]);
+      const bool placed = s.kind_class == 2 || (local(s.q2) && (s.q1 < 0 || local(s.q1)));
+      if (!dep && placed) {
+        ready.push_back(make_step(i, ST_GATE));
+        done_[i] = true;
+      } else {
+        blocked[s.q2] = true;
+        if (s.q1 >= 0) blocked[s.q1] = true;
+        any_blocked = true;
+      }
+    }
+  }
+
+  Step make_step(int i, int type) const {
+    Step st;
+    st.type = type;
+    st.inst = i;
+    st.p2 = map_[in_[i].q2];
+    st.p1 = in_[i].q1 >= 0 ? map_[in_[i].q1] : -1;
+    return st;
+  }
+
+  // ------------------------------------------------------------- tiling
+  bool tileable(const Step& st) const {
+    return st.type == ST_GATE && st.p2 < o_.n_loc && (st.p1 < 0 || st.p1 < o_.n_loc);
+  }
+
+  void emit(Plan& plan, const std::vector<Step>& ready) {
+    if (o_.tile_bits <= 0) {
+      for (const Step& st : ready) plan.steps.push_back(st);
+      return;
+    }
+    // Greedy grouping in the given (dependency-respecting) order.  A gate may
+    // join the open tile if the union of bit sets still fits; a gate that does
+    // not fit closes the tile only if it shares a qubit with a gate already
+    // deferred... to stay exact and simple we keep strict order: a non-fitting
+    // gate is deferred to the next tile together with everything that depends
+    // on it (tracked per physical position).
+    std::vector<Step> pending(ready.begin(), ready.end());
+    while (!pending.empty()) {
+      std::vector<int> bits;  // high bits (>= low_bits) of the open tile
+      std::vector<Step> in_tile, deferred;
+      std::vector<bool> dirty(o_.n, false);  // positions touched by a deferred step
+      const int cap = o_.tile_bits - o_.low_bits;
+      for (const Step& st : pending) {
+        bool dep = false;
+        auto touches = [&](int p) { return p >= 0 && p < o_.n && dirty[p]; };
+        if (touches(st.p2) || touches(st.p1)) dep = true;
+        bool fits = false;
+        if (!dep && tileable(st) && (int)in_tile.size() < o_.max_tile_gates) {
+          int extra = 0;
+          auto need = [&](int p) {
+            if (p < 0 || p < o_.low_bits) return;
+            if (std::find(bits.begin(), bits.end(), p) == bits.end()) extra++;
+          };
+          need(st.p2);
+          if (st.p1 != st.p2) need(st.p1);
+          if ((int)bits.size() + extra <= cap) {
+            fits = true;
+            auto add = [&](int p) {
+              if (p < 0 || p < o_.low_bits) return;
+              if (std::find(bits.begin(), bits.end(), p) == bits.end()) bits.push_back(p);
+            };
+            add(st.p2);
+            add(st.p1);
+          }
+        }
+        if (fits) {
+          in_tile.push_back(st);
+        } else if (!dep && !tileable(st) && in_tile.empty() && deferred.empty()) {
+          // a non-tileable step (density, global-diagonal) at the head runs on its own
+          plan.steps.push_back(st);
+        } else {
+          deferred.push_back(st);
+          if (st.type == ST_DENS) {
+            // densities are barriers: nothing after them may be pulled forward
+            for (int p = 0; p < o_.n; p++) dirty[p] = true;
+          } else {
+            if (st.p2 >= 0) dirty[st.p2] = true;
+            if (st.p1 >= 0) dirty[st.p1] = true;
+          }
+        }
+      }
+      if ((int)in_tile.size() >= o_.min_tile_gates) {
+        Step t;
+        t.type = ST_TILE;
+        t.first = (int)plan.tile_steps.size();
+        t.count = (int)in_tile.size();
+        for (const Step& st : in_tile) plan.tile_steps.push_back(st);
+        std::sort(bits.begin(), bits.end());
+        t.tb_first = (int)plan.tile_bits.size();
+        for (int l = 0; l < o_.low_bits; l++) plan.tile_bits.push_back(l);
+        for (int b : bits) plan.tile_bits.push_back(b);
+        t.tb_count = (int)plan.tile_bits.size() - t.tb_first;
+        plan.steps.push_back(t);
+      } else {
+        for (const Step& st : in_tile) plan.steps.push_back(st);
+      }
+      pending.swap(deferred);
+    }
+  }
+
+  // --------------------------------------------------------------- remap
+  // index (program order) of the first unfinished instruction using qubit q
+  std::vector<int> next_use() const {
+    const int N = (int)in_.size();
+    std::vector<int> nu(o_.n, N + 1);
+    for (int i = N - 1; i >= 0; i--) {
+      if (done_[i]) continue;
+      nu[in_[i].q2] = i;
+      if (in_[i].q1 >= 0) nu[in_[i].q1] = i;
+    }
+    return nu;
+  }
+
+  bool remap(Plan& plan) {
+    if (o_.n_loc >= o_.n) return false;
+    const std::vector<int> nu = next_use();
+    std::vector<int> globals, locals;
+    for (int q = 0; q < o_.n; q++) (local(q) ? locals : globals).push_back(q);
+    std::sort(globals.begin(), globals.end(), [&](int a, int b) { return nu[a] < nu[b]; });  // most urgent first
+    std::sort(locals.begin(), locals.end(), [&](int a, int b) {
+      if (nu[a] != nu[b]) return nu[a] > nu[b];  // least urgent first
+      return map_[a] > map_[b];                  // prefer high positions (cheaper, contiguous halves)
+    });
+    bool any = false;
+    for (size_t k = 0; k < globals.size() && k < locals.size(); k++) {
+      const int G = globals[k], L = locals[k];
+      if (!(nu[G] < nu[L])) break;
+      Step st;
+      st.type = ST_SWAP;
+      st.gbit = map_[G] - o_.n_loc;
+      st.lpos = map_[L];
+      plan.steps.push_back(st);
+      std::swap(map_[G], map_[L]);
+      any = true;
+    }
+    return any;
+  }
+};
+
+}  // namespace qdc

@@ -1,0 +1,585 @@
+// Tiled multi-gate passes: several gates per HBM round trip.
+//
+// A pass fixes a set of T physical bit positions (the low L bits, so that every
+// global access is a >= 128-byte contiguous run, plus T-L arbitrary higher
+// positions).  The 2^n state decomposes into 2^(n-T) independent tiles of 2^T
+// amplitudes; a persistent CTA loads a tile into shared memory with coalesced
+// 128-bit accesses, applies EVERY gate of the pass in shared memory (128-bit
+// LDS/STS, gate matrices read from the kernel-parameter constant bank, so FFMAs
+// take constant operands), and writes the tile back once.
+//
+//   forward : 2*S bytes for the whole group instead of 2*S per gate.
+//   backward: the tile holds state AND adjoint; per gate (reverse order)
+//             fwd <- U^-1 fwd, grad += bwd (x) fwd, bwd <- U^T bwd; gradient
+//             partials are reduced warp -> CTA (deterministic order) and kept
+//             in shared memory across the CTA's tiles; 4*S bytes per group
+//             instead of 4*S (reference: 6*S, src/circuit.rs:320-333) per gate.
+//
+// Once a pass holds more than ~4 gates the kernel leaves the HBM-bound regime
+// and becomes FP32/FP64-pipe bound (16 FMA per amplitude per 2-qubit gate).
+#pragma once
+#include "circuit.cuh"
+
+#define QDC_TILE_NT_F 256  // threads per CTA, forward tile kernel (3 CTAs / SM)
+#define QDC_TILE_NT_B 128  // backward tile kernel: fewer threads, more registers each (3 CTAs / SM)
+
+#ifdef QDC_F64
+#define QDC_TILE_MAXG_F 48
+#define QDC_TILE_MAXG_B 24
+#else
+#define QDC_TILE_MAXG_F 64
+#define QDC_TILE_MAXG_B 32
+#endif
+
+// out = OR_k ((x >> src_k) & (2^width_k - 1)) << dst_k : a software bit-deposit
+struct BitDeposit {
+  int nseg;
+  unsigned char src[8], dst[8], width[8];
+  __host__ __device__ __forceinline__ uint64_t operator()(uint64_t x) const {
+    uint64_t out = 0;
+    for (int k = 0; k < nseg; k++) out |= ((x >> src[k]) & ((1ull << width[k]) - 1ull)) << dst[k];
+    return out;
+  }
+};
+
+static inline bool make_deposit(const std::vector<int>& positions, BitDeposit* d) {
+  d->nseg = 0;
+  size_t i = 0;
+  while (i < positions.size()) {
+    size_t j = i + 1;
+    while (j < positions.size() && positions[j] == positions[j - 1] + 1) j++;
+    if (d->nseg == 8) return false;
+    d->src[d->nseg] = (unsigned char)i;
+    d->dst[d->nseg] = (unsigned char)positions[i];
+    d->width[d->nseg] = (unsigned char)(j - i);
+    d->nseg++;
+    i = j;
+  }
+  return true;
+}
+
+struct TileGeo {
+  int T, L;
+  BitDeposit hi;    // run index within the tile (T-L bits) -> amplitude offset
+  BitDeposit tile;  // tile number (n-T bits)               -> amplitude base
+  uint64_t ntiles;
+};
+
+enum { TG_Q1 = 0, TG_Q2 = 1, TG_DIAG = 2 };
+
+struct TileGateF {  // one matrix
+  int type, a, b, pad;  // tile-local bits; q2: a > b and the matrix is in (a,b) order; diag: j = 2 bit(a) + bit(b)
+  real_t re[16], im[16];
+};
+struct TileGateB {  // inverse (for the state) and transpose (for the adjoint)
+  int type, a, b, slot;  // slot < 0: constant gate (no gradient)
+  real_t ire[16], iim[16], tre[16], tim[16];
+};
+struct TileFwdParams {
+  TileGeo geo;
+  int ngates;
+  TileGateF g[QDC_TILE_MAXG_F];
+};
+struct TileBwdParams {
+  TileGeo geo;
+  int ngates;
+  TileGateB g[QDC_TILE_MAXG_B];
+};
+
+// ------------------------------------------------------------ tile <-> HBM
+template <int NT, bool LOAD>
+__device__ __forceinline__ void tile_io(vec_t* __restrict__ gmem, vec_t* __restrict__ smv, const TileGeo& geo,
+                                        uint64_t tile) {
+  const int nvec = 1 << (geo.T - QDC_LV);
+  const int runv_log = geo.L - QDC_LV;
+  const uint64_t base = geo.tile(tile) >> QDC_LV;
+  const int tid = threadIdx.x;
+  // v = tid + i * NT; run index r = v >> runv_log splits into disjoint thread / iteration bits
+  const uint64_t off_lo = (geo.hi((uint64_t)(tid >> runv_log)) >> QDC_LV) + (uint64_t)(tid & ((1 << runv_log) - 1));
+  constexpr int UNR = 4;
+  for (int i0 = 0; i0 < nvec / NT; i0 += UNR) {
+    vec_t tmp[UNR];
+    uint64_t g[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; u++) {
+      const int i = i0 + u;
+      g[u] = base + off_lo + (geo.hi((uint64_t)i * (NT >> runv_log)) >> QDC_LV);
+      if (LOAD && i < nvec / NT) tmp[u] = gmem[g[u]];
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; u++) {
+      const int i = i0 + u;
+      if (i < nvec / NT) {
+        const int v = tid + i * NT;
+        if (LOAD) smv[v] = tmp[u]; else gmem[g[u]] = smv[v];
+      }
+    }
+  }
+}
+
+// ------------------------------------------------- in-tile gate application
+template <int K>
+__device__ __forceinline__ void mv(const real_t (&gre)[16], const real_t (&gim)[16], cplx_t (&a)[K]) {
+  cplx_t o[K];
+#pragma unroll
+  for (int r = 0; r < K; r++) {
+    o[r].x = 0;
+    o[r].y = 0;
+#pragma unroll
+    for (int c = 0; c < K; c++) cmac(o[r], gre[r * K + c], gim[r * K + c], a[c]);
+  }
+#pragma unroll
+  for (int r = 0; r < K; r++) a[r] = o[r];
+}
+
+// forward: a <- G a over every item of geometry Geo in the shared tile
+template <int NT, class Geo>
+__device__ __forceinline__ void tile_apply(vec_t* smv, const Geo& geo, int nitems, const TileGateF& G) {
+  constexpr int K = Geo::K;
+  for (int i = threadIdx.x; i < nitems; i += NT) {
+    VecU v[Geo::NVEC];
+    const uint32_t base = (uint32_t)geo.base((uint64_t)i);
+#pragma unroll
+    for (int c = 0; c < Geo::NVEC; c++) v[c].v = smv[base + (uint32_t)geo.off(c)];
+    cplx_t a[Geo::NG][K];
+    Geo::unpack(v, a);
+#pragma unroll
+    for (int e = 0; e < Geo::NG; e++) mv<K>(G.re, G.im, a[e]);
+    Geo::pack(v, a);
+#pragma unroll
+    for (int c = 0; c < Geo::NVEC; c++) smv[base + (uint32_t)geo.off(c)] = v[c].v;
+  }
+}
+
+template <int NT>
+__device__ __forceinline__ void tile_diag(vec_t* smv, int nvec, const real_t (&dre)[16], const real_t (&dim)[16],
+                                          int a, int b) {
+  for (int i = threadIdx.x; i < nvec; i += NT) {
+    VecU v;
+    v.v = smv[i];
+#pragma unroll
+    for (int e = 0; e < QDC_VA; e++) {
+      const int amp = i * QDC_VA + e;
+      const int j = 2 * ((amp >> a) & 1) + ((amp >> b) & 1);
+      const real_t dr = sel4(dre, j), di = sel4(dim, j);
+      const real_t x = v.r[2 * e] * dr - v.r[2 * e + 1] * di, y = v.r[2 * e] * di + v.r[2 * e + 1] * dr;
+      v.r[2 * e] = x;
+      v.r[2 * e + 1] = y;
+    }
+    smv[i] = v.v;
+  }
+}
+
+__global__ void __launch_bounds__(QDC_TILE_NT_F, 3)
+    k_tile_fwd(cplx_t* __restrict__ state, const __grid_constant__ TileFwdParams p) {
+  extern __shared__ __align__(16) unsigned char tile_smem[];
+  vec_t* smv = (vec_t*)tile_smem;
+  const int nvec = 1 << (p.geo.T - QDC_LV);
+  for (uint64_t tile = blockIdx.x; tile < p.geo.ntiles; tile += gridDim.x) {
+    tile_io<QDC_TILE_NT_F, true>((vec_t*)state, smv, p.geo, tile);
+    __syncthreads();
+    for (int g = 0; g < p.ngates; g++) {
+      const TileGateF& G = p.g[g];
+      if (G.type == TG_Q2) {
+#ifndef QDC_F64
+        if (G.b == 0) {
+          GeoQ2LH geo;
+          geo.hv = G.a - 1;
+          tile_apply<QDC_TILE_NT_F>(smv, geo, nvec / 2, G);
+        } else
+#endif
+        {
+          GeoQ2HH geo;
+          geo.lv = G.b - QDC_LV;
+          geo.hv = G.a - QDC_LV;
+          tile_apply<QDC_TILE_NT_F>(smv, geo, nvec / 4, G);
+        }
+      } else if (G.type == TG_Q1) {
+#ifndef QDC_F64
+        if (G.a == 0) {
+          GeoQ1L geo;
+          tile_apply<QDC_TILE_NT_F>(smv, geo, nvec, G);
+        } else
+#endif
+        {
+          GeoQ1H geo;
+          geo.pv = G.a - QDC_LV;
+          tile_apply<QDC_TILE_NT_F>(smv, geo, nvec / 2, G);
+        }
+      } else {
+        tile_diag<QDC_TILE_NT_F>(smv, nvec, G.re, G.im, G.a, G.b);
+      }
+      __syncthreads();
+    }
+    tile_io<QDC_TILE_NT_F, false>((vec_t*)state, smv, p.geo, tile);
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------- backward
+template <int NT, class Geo>
+__device__ __forceinline__ void tile_rev(vec_t* smf, vec_t* smb, const Geo& geo, int nitems, const TileGateB& G,
+                                         real_t* acc) {
+  constexpr int K = Geo::K;
+  // phase A: un-compute the state.  Phase B revisits the same items with the
+  // same thread, so no barrier is needed in between; splitting keeps only one
+  // gate matrix live at a time (register pressure).
+  for (int i = threadIdx.x; i < nitems; i += NT) {
+    VecU vf[Geo::NVEC];
+    const uint32_t base = (uint32_t)geo.base((uint64_t)i);
+#pragma unroll
+    for (int c = 0; c < Geo::NVEC; c++) vf[c].v = smf[base + (uint32_t)geo.off(c)];
+    cplx_t a[Geo::NG][K];
+    Geo::unpack(vf, a);
+#pragma unroll
+    for (int e = 0; e < Geo::NG; e++) mv<K>(G.ire, G.iim, a[e]);
+    Geo::pack(vf, a);
+#pragma unroll
+    for (int c = 0; c < Geo::NVEC; c++) smf[base + (uint32_t)geo.off(c)] = vf[c].v;
+  }
+  // phase B: gradient from (pre-gate state, post-gate adjoint), then pull the adjoint back
+  for (int i = threadIdx.x; i < nitems; i += NT) {
+    VecU vf[Geo::NVEC], vb[Geo::NVEC];
+    const uint32_t base = (uint32_t)geo.base((uint64_t)i);
+#pragma unroll
+    for (int c = 0; c < Geo::NVEC; c++) {
+      vb[c].v = smb[base + (uint32_t)geo.off(c)];
+      if (G.slot >= 0) vf[c].v = smf[base + (uint32_t)geo.off(c)];
+    }
+    cplx_t b[Geo::NG][K];
+    Geo::unpack(vb, b);
+    if (G.slot >= 0) {
+      cplx_t a[Geo::NG][K];
+      Geo::unpack(vf, a);
+#pragma unroll
+      for (int e = 0; e < Geo::NG; e++) outer_acc<K>(b[e], a[e], acc);
+    }
+#pragma unroll
+    for (int e = 0; e < Geo::NG; e++) mv<K>(G.tre, G.tim, b[e]);
+    Geo::pack(vb, b);
+#pragma unroll
+    for (int c = 0; c < Geo::NVEC; c++) smb[base + (uint32_t)geo.off(c)] = vb[c].v;
+  }
+}
+
+template <int NT>
+__device__ __forceinline__ void tile_rev_diag(vec_t* smf, vec_t* smb, int nvec, const TileGateB& G, real_t* acc) {
+  for (int i = threadIdx.x; i < nvec; i += NT) {
+    VecU vf, vb;
+    vf.v = smf[i];
+    vb.v = smb[i];
+#pragma unroll
+    for (int e = 0; e < QDC_VA; e++) {
+      const int amp = i * QDC_VA + e;
+      const int j = 2 * ((amp >> G.a) & 1) + ((amp >> G.b) & 1);
+      real_t dr = sel4(G.ire, j), di = sel4(G.iim, j);
+      const real_t fx = vf.r[2 * e] * dr - vf.r[2 * e + 1] * di, fy = vf.r[2 * e] * di + vf.r[2 * e + 1] * dr;
+      vf.r[2 * e] = fx;
+      vf.r[2 * e + 1] = fy;
+      const real_t bx = vb.r[2 * e], by = vb.r[2 * e + 1];
+      if (G.slot >= 0) {
+        const real_t pr = bx * fx - by * fy, pi = bx * fy + by * fx;
+#pragma unroll
+        for (int jj = 0; jj < 4; jj++) {
+          acc[2 * jj] += (j == jj) ? pr : (real_t)0;
+          acc[2 * jj + 1] += (j == jj) ? pi : (real_t)0;
+        }
+      }
+      dr = sel4(G.tre, j);
+      di = sel4(G.tim, j);
+      vb.r[2 * e] = bx * dr - by * di;
+      vb.r[2 * e + 1] = bx * di + by * dr;
+    }
+    smf[i] = vf.v;
+    smb[i] = vb.v;
+  }
+}
+
+// partials: [gridDim.x][ngates][32] doubles
+__global__ void __launch_bounds__(QDC_TILE_NT_B, 3)
+    k_tile_bwd(cplx_t* __restrict__ fwd, cplx_t* __restrict__ bwd, const __grid_constant__ TileBwdParams p,
+               double* __restrict__ partials) {
+  extern __shared__ __align__(16) unsigned char tile_smem[];
+  const int nvec = 1 << (p.geo.T - QDC_LV);
+  vec_t* smf = (vec_t*)tile_smem;
+  vec_t* smb = smf + nvec;
+  double* sm_acc = (double*)(smb + nvec);                    // [MAXG_B][32]
+  real_t* sm_part = (real_t*)(sm_acc + QDC_TILE_MAXG_B * 32);  // [2][warps][32]
+  constexpr int NW = QDC_TILE_NT_B / 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < QDC_TILE_MAXG_B * 32; i += QDC_TILE_NT_B) sm_acc[i] = 0.0;
+  __syncthreads();
+  for (uint64_t tile = blockIdx.x; tile < p.geo.ntiles; tile += gridDim.x) {
+    tile_io<QDC_TILE_NT_B, true>((vec_t*)fwd, smf, p.geo, tile);
+    tile_io<QDC_TILE_NT_B, true>((vec_t*)bwd, smb, p.geo, tile);
+    __syncthreads();
+    for (int g = 0; g < p.ngates; g++) {
+      const TileGateB& G = p.g[g];
+      real_t acc[32];
+#pragma unroll
+      for (int k = 0; k < 32; k++) acc[k] = 0;
+      if (G.type == TG_Q2) {
+#ifndef QDC_F64
+        if (G.b == 0) {
+          GeoQ2LH geo;
+          geo.hv = G.a - 1;
+          tile_rev<QDC_TILE_NT_B>(smf, smb, geo, nvec / 2, G, acc);
+        } else
+#endif
+        {
+          GeoQ2HH geo;
+          geo.lv = G.b - QDC_LV;
+          geo.hv = G.a - QDC_LV;
+          tile_rev<QDC_TILE_NT_B>(smf, smb, geo, nvec / 4, G, acc);
+        }
+      } else if (G.type == TG_Q1) {
+#ifndef QDC_F64
+        if (G.a == 0) {
+          GeoQ1L geo;
+          tile_rev<QDC_TILE_NT_B>(smf, smb, geo, nvec, G, acc);
+        } else
+#endif
+        {
+          GeoQ1H geo;
+          geo.pv = G.a - QDC_LV;
+          tile_rev<QDC_TILE_NT_B>(smf, smb, geo, nvec / 2, G, acc);
+        }
+      } else {
+        tile_rev_diag<QDC_TILE_NT_B>(smf, smb, nvec, G, acc);
+      }
+      real_t* part = sm_part + (size_t)(g & 1) * NW * 32;
+      if (G.slot >= 0) {
+        double d = 0.0;
+        warp_flush<32>(acc, d, lane);  // lane j now holds the warp total of value j
+        part[warp * 32 + lane] = (real_t)d;
+      }
+      __syncthreads();
+      if (G.slot >= 0 && warp == 0) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < NW; w++) s += (double)part[w * 32 + lane];
+        sm_acc[g * 32 + lane] += s;
+      }
+    }
+    tile_io<QDC_TILE_NT_B, false>((vec_t*)fwd, smf, p.geo, tile);
+    tile_io<QDC_TILE_NT_B, false>((vec_t*)bwd, smb, p.geo, tile);
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < p.ngates * 32; i += QDC_TILE_NT_B)
+    partials[(size_t)blockIdx.x * p.ngates * 32 + i] = sm_acc[i];
+}
+
+// out[slot(g)][j] += sum_cta partials[cta][g][j]    (one block per gate, 32 threads)
+struct TileSlots {
+  int s[QDC_TILE_MAXG_B];
+};
+__global__ void k_tile_final(const double* __restrict__ partials, int ncta, int ngates, const TileSlots slots,
+                             double* __restrict__ out) {
+  const int g = blockIdx.x, j = threadIdx.x;
+  const int slot = slots.s[g];
+  if (slot < 0) return;
+  double s = 0;
+  for (int c = 0; c < ncta; c++) s += partials[((size_t)c * ngates + g) * 32 + j];
+  out[(size_t)slot * 32 + j] += s;
+}
+
+// ------------------------------------------------------------ host launch
+static inline const char* make_tile_geo(const qdc::Plan& plan, const qdc::Step& t, int n_loc, int low_bits,
+                                        TileGeo* geo, std::vector<int>* tile_pos_of) {
+  std::vector<int> bits(plan.tile_bits.begin() + t.tb_first, plan.tile_bits.begin() + t.tb_first + t.tb_count);
+  // pad with the lowest unused positions so that T >= log2(threads * vector) and runs stay whole
+  int T = (int)bits.size();
+  const int min_T = QDC_LV + 8 + 2;  // every thread gets at least one 4-vector quad item
+  for (int p = 0; T < min_T && p < n_loc; p++) {
+    if (std::find(bits.begin(), bits.end(), p) == bits.end()) {
+      bits.push_back(p);
+      T++;
+    }
+  }
+  std::sort(bits.begin(), bits.end());
+  if (T < min_T) return qdc_errf("register too small for a tiled pass.");
+  int L = 0;
+  while (L < T && bits[L] == L) L++;
+  if (L < low_bits && L < T) return qdc_errf("tile does not contain the low bits.");
+  if (L > T - 1) L = T - 1;
+  // run = the low L contiguous bits; cap so that a run does not exceed one thread-row
+  const int maxL = QDC_LV + 7;  // vectors per run <= threads of the narrower (backward) kernel
+  if (L > maxL) L = maxL;
+  geo->T = T;
+  geo->L = L;
+  std::vector<int> hi(bits.begin() + L, bits.end());
+  std::vector<int> rest;
+  for (int p = 0; p < n_loc; p++)
+    if (std::find(bits.begin(), bits.end(), p) == bits.end()) rest.push_back(p);
+  if (!make_deposit(hi, &geo->hi) || !make_deposit(rest, &geo->tile))
+    return qdc_errf("tile bit set too fragmented.");
+  geo->ntiles = 1ull << (n_loc - T);
+  tile_pos_of->assign(n_loc, -1);
+  for (int k = 0; k < T; k++) (*tile_pos_of)[bits[k]] = k;
+  return nullptr;
+}
+
+inline void Circuit::release_tiles() {
+  if (tile_partials_) cudaFree(tile_partials_);
+  tile_partials_ = nullptr;
+  tile_partials_cap_ = 0;
+}
+
+static inline const char* tile_grid(const void* kernel, int threads, size_t smem, uint64_t ntiles, int* grid) {
+  DeviceInfo di;
+  QDC_TRY(qdc_device_info(&di));
+  QDC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int bps = 0;
+  QDC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kernel, threads, smem));
+  if (bps < 1) return qdc_errf("tile kernel does not fit on an SM (%zu bytes of shared memory).", smem);
+  const uint64_t cap = (uint64_t)di.sm_count * bps;
+  *grid = (int)(ntiles < cap ? ntiles : cap);
+  return nullptr;
+}
+
+// Fill the (hi,lo)-ordered matrix of a dense gate, or the 4 diagonal entries.
+static inline const char* tile_matrix(const cplx_t* gate, int kind, int form, bool swap, real_t* re, real_t* im) {
+  for (int i = 0; i < 16; i++) re[i] = im[i] = 0;
+  if (kind_is_q1(kind)) {
+    zc m[4];
+    QDC_TRY(make_form<2>(gate, form, m));
+    split<4>(m, re, im);
+  } else if (kind_is_q2dense(kind)) {
+    zc m[16];
+    QDC_TRY(make_form<4>(gate, form, m));
+    to_hilo(m, swap);
+    split<16>(m, re, im);
+  } else {
+    for (int j = 0; j < 4; j++) {
+      re[j] = gate[j].x;
+      im[j] = (form == FORM_CONJ_TR) ? -gate[j].y : gate[j].y;
+    }
+  }
+  return nullptr;
+}
+
+inline const char* Circuit::run_tile_forward(const qdc::Step& t, const std::vector<const cplx_t*>& gp) {
+  static thread_local TileFwdParams p;  // large: keep off the stack
+  std::vector<int> tpos;
+  QDC_TRY(make_tile_geo(plan_, t, n_loc_, 0, &p.geo, &tpos));
+  if (t.count > QDC_TILE_MAXG_F) return qdc_errf("tile pass holds too many gates.");
+  p.ngates = t.count;
+  for (int k = 0; k < t.count; k++) {
+    const qdc::Step& st = plan_.tile_steps[t.first + k];
+    const int kind = insts_[st.inst].kind;
+    TileGateF& G = p.g[k];
+    G.pad = 0;
+    const bool swap = st.p1 >= 0 && st.p2 < st.p1;
+    QDC_TRY(tile_matrix(gp[st.inst], kind, FORM_PLAIN, swap, G.re, G.im));
+    if (kind_is_q1(kind)) {
+      G.type = TG_Q1;
+      G.a = tpos[st.p2];
+      G.b = -1;
+    } else if (kind_is_q2dense(kind)) {
+      G.type = TG_Q2;
+      G.a = tpos[swap ? st.p1 : st.p2];
+      G.b = tpos[swap ? st.p2 : st.p1];
+    } else {
+      G.type = TG_DIAG;
+      G.a = tpos[st.p2];
+      G.b = tpos[st.p1];
+    }
+  }
+  const size_t smem = sizeof(cplx_t) << p.geo.T;
+  int grid = 0;
+  QDC_TRY(tile_grid((const void*)k_tile_fwd, QDC_TILE_NT_F, smem, p.geo.ntiles, &grid));
+  cudaEvent_t pa = nullptr;
+  if (prof_.on) pa = prof_.begin(stream_);
+  k_tile_fwd<<<grid, QDC_TILE_NT_F, smem, stream_>>>(state_, p);
+  QDC_CUDA(cudaGetLastError());
+  if (prof_.on) prof_.end(stream_, CAT_TILE_FWD, pa, 2ull * t.count * bytes());
+  stats_.kernel_launches += 1;
+  stats_.hbm_passes += 1;
+  stats_.algorithmic_bytes += 2ull * t.count * bytes();
+  return nullptr;
+}
+
+inline const char* Circuit::run_tile_backward(const qdc::Step& t, const std::vector<const cplx_t*>& gp,
+                                              const std::vector<long>& vslot, bool live) {
+  if (!live) {
+    // no adjoint yet: un-compute the group with the forward kernel (inverse matrices, reverse order)
+    static thread_local TileFwdParams p;
+    std::vector<int> tpos;
+    QDC_TRY(make_tile_geo(plan_, t, n_loc_, 0, &p.geo, &tpos));
+    p.ngates = t.count;
+    for (int k = 0; k < t.count; k++) {
+      const qdc::Step& st = plan_.tile_steps[t.first + t.count - 1 - k];
+      const int kind = insts_[st.inst].kind;
+      TileGateF& G = p.g[k];
+      G.pad = 0;
+      const bool swap = st.p1 >= 0 && st.p2 < st.p1;
+      QDC_TRY(tile_matrix(gp[st.inst], kind, kind_is_nonu(kind) ? FORM_INV : FORM_CONJ_TR, swap, G.re, G.im));
+      G.type = kind_is_q1(kind) ? TG_Q1 : (kind_is_q2dense(kind) ? TG_Q2 : TG_DIAG);
+      if (G.type == TG_Q2) {
+        G.a = tpos[swap ? st.p1 : st.p2];
+        G.b = tpos[swap ? st.p2 : st.p1];
+      } else {
+        G.a = tpos[st.p2];
+        G.b = st.p1 >= 0 ? tpos[st.p1] : -1;
+      }
+    }
+    const size_t smem = sizeof(cplx_t) << p.geo.T;
+    int grid = 0;
+    QDC_TRY(tile_grid((const void*)k_tile_fwd, QDC_TILE_NT_F, smem, p.geo.ntiles, &grid));
+    cudaEvent_t pa = nullptr;
+    if (prof_.on) pa = prof_.begin(stream_);
+    k_tile_fwd<<<grid, QDC_TILE_NT_F, smem, stream_>>>(state_, p);
+    QDC_CUDA(cudaGetLastError());
+    if (prof_.on) prof_.end(stream_, CAT_UNCOMPUTE, pa, 2ull * t.count * bytes());
+    stats_.kernel_launches += 1;
+    stats_.hbm_passes += 1;
+    stats_.algorithmic_bytes += 2ull * t.count * bytes();
+    return nullptr;
+  }
+  static thread_local TileBwdParams p;
+  std::vector<int> tpos;
+  QDC_TRY(make_tile_geo(plan_, t, n_loc_, 0, &p.geo, &tpos));
+  if (t.count > QDC_TILE_MAXG_B) return qdc_errf("tile pass holds too many gates for the backward kernel.");
+  p.ngates = t.count;
+  TileSlots h_slots;
+  for (int k = 0; k < t.count; k++) {
+    const qdc::Step& st = plan_.tile_steps[t.first + t.count - 1 - k];
+    const int kind = insts_[st.inst].kind;
+    TileGateB& G = p.g[k];
+    const bool swap = st.p1 >= 0 && st.p2 < st.p1;
+    QDC_TRY(tile_matrix(gp[st.inst], kind, kind_is_nonu(kind) ? FORM_INV : FORM_CONJ_TR, swap, G.ire, G.iim));
+    QDC_TRY(tile_matrix(gp[st.inst], kind, kind_is_diag(kind) ? FORM_PLAIN : FORM_TR, swap, G.tre, G.tim));
+    G.type = kind_is_q1(kind) ? TG_Q1 : (kind_is_q2dense(kind) ? TG_Q2 : TG_DIAG);
+    if (G.type == TG_Q2) {
+      G.a = tpos[swap ? st.p1 : st.p2];
+      G.b = tpos[swap ? st.p2 : st.p1];
+    } else {
+      G.a = tpos[st.p2];
+      G.b = st.p1 >= 0 ? tpos[st.p1] : -1;
+    }
+    G.slot = (int)vslot[st.inst];
+    h_slots.s[k] = G.slot;
+  }
+  const size_t tile_bytes = sizeof(cplx_t) << p.geo.T;
+  const size_t smem = 2 * tile_bytes + QDC_TILE_MAXG_B * 32 * sizeof(double) +
+                      2 * (QDC_TILE_NT_B / 32) * 32 * sizeof(real_t);
+  int grid = 0;
+  QDC_TRY(tile_grid((const void*)k_tile_bwd, QDC_TILE_NT_B, smem, p.geo.ntiles, &grid));
+  const size_t need = (size_t)grid * QDC_TILE_MAXG_B * 32;
+  if (need > tile_partials_cap_) {
+    if (tile_partials_) QDC_CUDA(cudaFree(tile_partials_));
+    QDC_CUDA(cudaMalloc((void**)&tile_partials_, need * sizeof(double)));
+    tile_partials_cap_ = need;
+  }
+  cudaEvent_t pa = nullptr;
+  if (prof_.on) pa = prof_.begin(stream_);
+  k_tile_bwd<<<grid, QDC_TILE_NT_B, smem, stream_>>>(state_, bwd_, p, tile_partials_);
+  QDC_CUDA(cudaGetLastError());
+  k_tile_final<<<t.count, 32, 0, stream_>>>(tile_partials_, grid, t.count, h_slots, d_res_);
+  QDC_CUDA(cudaGetLastError());
+  if (prof_.on) prof_.end(stream_, CAT_TILE_BWD, pa, 4ull * t.count * bytes());
+  stats_.kernel_launches += 2;
+  stats_.hbm_passes += 2;
+  stats_.algorithmic_bytes += 4ull * t.count * bytes();
+  return nullptr;
+}

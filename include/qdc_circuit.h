@@ -51,6 +51,18 @@ enum qdc_count {
 /* Circuit::new, src/circuit.rs:95-103 (state |0..0>; the initial-state copy is
  * materialised lazily, only after set_state_from_host). */
 const char* qdc_circuit_new(qdc_circuit** out, size_t qubits_number);
+/* Sharded construction (no counterpart in the reference, which is single-GPU):
+ * rank r of world = 2^g ranks owns the amplitudes whose top g index bits equal
+ * r (the top g PHYSICAL positions are "global").  Gates on local positions and
+ * diagonal gates run without communication; a dense gate or a density on a
+ * global qubit triggers a qubit-remap swap = one half-shard exchange with the
+ * partner rank (NCCL point-to-point over NVLink).  `nccl_unique_id` is the 128
+ * byte id from qdc_nccl_unique_id() on rank 0, distributed by the caller.
+ * set_state_from_host takes this rank's shard; run/forward/backward return
+ * this rank's PARTIAL densities / gradients: the caller sums them over ranks. */
+const char* qdc_circuit_new_sharded(qdc_circuit** out, size_t qubits_number, int rank, int world,
+                                    const void* nccl_unique_id);
+const char* qdc_nccl_unique_id(void* out128);
 const char* qdc_circuit_free(qdc_circuit* c);
 /* Circuit::set_state_from_vector, src/circuit.rs:104-106 */
 const char* qdc_circuit_set_state_from_host(qdc_circuit* c, const qdc_complex* host_state, size_t len);
@@ -86,7 +98,8 @@ const char* qdc_circuit_state_device_ptr(qdc_circuit* c, void** device_ptr);
 /* Run on a caller-provided cudaStream_t (default: the legacy default stream). */
 const char* qdc_circuit_set_stream(qdc_circuit* c, void* cuda_stream);
 /* Tunables: "fuse" (0 = one pass per instruction, 1 = tiled multi-gate passes),
- * "profile" (1 = time every launch group with CUDA events). */
+ * "profile" (1 = time every launch group with CUDA events), "tile_bits",
+ * "low_bits", "max_tile_gates" (geometry of the tiled passes; 0 = default). */
 const char* qdc_circuit_set_option(qdc_circuit* c, const char* key, long value);
 /* Execution statistics of the last run/forward/backward call. */
 typedef struct {
@@ -106,6 +119,18 @@ typedef struct {
 int qdc_profile_categories(void);
 const char* qdc_profile_category_name(int category);
 const char* qdc_circuit_last_profile(const qdc_circuit* c, int category, qdc_profile_entry* out);
+
+/* The pass scheduler as a pure function (no device needed): turns an
+ * instruction list into the plan the executor would run for `n` qubits of which
+ * `n_loc` are local (n_loc == n: single GPU), with tiled multi-gate passes over
+ * `tile_bits` positions (0: none) that always include the `low_bits` lowest.
+ * Encoding (int64): per step [type, inst, p2, p1, gbit, lpos, count, nbits]
+ * (type 0 gate, 1 density, 2 swap of global bit `gbit` with local position
+ * `lpos`, 3 tile pass), a tile pass being followed by count x [inst, p2, p1]
+ * and nbits x [position]; terminated by [-1, n, final_map[0..n-1]]. */
+const char* qdc_schedule(size_t n, size_t n_loc, int tile_bits, int low_bits, int max_tile_gates,
+                         const int* kinds, const size_t* pos2, const size_t* pos1, size_t count,
+                         int all_densities, int64_t* out, size_t capacity, size_t* out_len);
 
 /* Fused single reverse step on DEVICE buffers (the 4*S kernel):
  * fwd <- U^dagger fwd (or U^-1 fwd when non_unitary), grad (+)= sum bwd (x) fwd,

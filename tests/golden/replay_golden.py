@@ -25,12 +25,8 @@ def _split(flat, sizes):
 
 
 def circuit_layout(n, layers):
-    from test_oracle import autodiff_var_layout
-    half = (n - 1) // 2
-    const_sizes = []
-    for _ in range(layers):
-        const_sizes += [4] * n + [16] * half + [4] * half + [4] * n + [16] * half
-    return const_sizes, autodiff_var_layout(n, layers)
+    from test_oracle import autodiff_const_layout, autodiff_var_layout
+    return autodiff_const_layout(n, layers), autodiff_var_layout(n, layers)
 
 
 def check_oracle_against_golden(path):

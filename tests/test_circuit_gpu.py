@@ -49,10 +49,11 @@ def test_every_instruction_kind_matches_oracle(pkg, dtype, fuse):
     """Circuit of src/test_autodiff.py:51-81 (all 14 instruction kinds): densities
     of run/forward and all gate gradients vs the oracle VM."""
     from quantum_differentiable_circuit import Circuit
-    n, layers = 9, 2
+    n, layers = (13, 2) if fuse else (9, 2)
     rng = np.random.default_rng(42)
     c = Circuit(n, precision=prec(dtype))
     c.set_option("fuse", fuse)
+    c.set_option("tile_bits", 11)      # several tiles per pass at this small n
     o = OracleCircuit(n)
     init = np.zeros(1 << n, dtype=dtype); init[0] = 1
     c.set_state_from_vector(init)
@@ -73,6 +74,7 @@ def test_every_instruction_kind_matches_oracle(pkg, dtype, fuse):
         assert np.abs(g - go).max() / gscale < tol
     # the working state is back at the initial state (every gate un-computed)
     assert np.abs(c.get_cpu_state_copy() - init).max() < (1e-4 if dtype == np.complex64 else 1e-11)
+    assert c.last_profile() == {}  # profiling is opt-in
 
 
 @pytest.mark.parametrize("fuse", [0, 1])
@@ -84,6 +86,7 @@ def test_autodiff_finite_difference_f64(pkg, fuse):
     rng = np.random.default_rng(42)
     c = AutoGradCircuit(n, precision="f64")
     c.circuit.set_option("fuse", fuse)
+    c.circuit.set_option("tile_bits", 11)
     init = np.zeros(1 << n, dtype=np.complex128); init[0] = 1
     c.set_state_from_vector(init)
     build_autodiff_circuit(c, n, layers)
@@ -165,11 +168,12 @@ def tfim_h(dtype, field=1.0):
 def test_vqse_step_matches_oracle(pkg, dtype, fuse):
     """One value-and-grad of the TFIM ansatz (example_vqse_ising.py:52-113) at n = 10."""
     from quantum_differentiable_circuit import Circuit
-    n, layers = 10, 3
+    n, layers = (13, 3) if fuse else (10, 3)
     rng = np.random.default_rng(42)
     params = rng.normal(size=2 * layers)
     c = Circuit(n, precision=prec(dtype)); o = OracleCircuit(n)
     c.set_option("fuse", fuse)
+    c.set_option("tile_bits", 11)
     init = (np.ones(1 << n) / np.sqrt(1 << n)).astype(dtype)
     c.set_state_from_vector(init); o.set_state_from_vector(init)
     build_vqse(c, n, layers); build_vqse(o, n, layers)
@@ -223,7 +227,8 @@ def test_zero_gradient_before_first_seed_and_errors(pkg, dtype):
         c.set_state_from_vector(np.zeros(8, dtype=dtype))
 
 
-def test_f32_matches_f64_on_autodiff_20q(pkg):
+@pytest.mark.parametrize("fuse", [0, 1])
+def test_f32_matches_f64_on_autodiff_20q(pkg, fuse):
     """BASELINE.json configs[1]: 20-qubit layered circuit, f32 gradients vs the f64 build (<= 1e-5)."""
     from quantum_differentiable_circuit import Circuit
     n, layers = 20, 2
@@ -232,6 +237,7 @@ def test_f32_matches_f64_on_autodiff_20q(pkg):
     res = {}
     for dtype in DTYPES:
         c = Circuit(n, precision=prec(dtype))
+        c.set_option("fuse", fuse)
         build_autodiff_circuit(c, n, layers)
         cg, vg = [g.astype(dtype) for g in const], [g.astype(dtype) for g in var]
         dens = c.forward(cg, vg)
@@ -260,3 +266,28 @@ def test_large_index_ghz_31q(pkg):
     for p in (0, 16, n - 1):
         np.testing.assert_allclose(vm.get_q1_density(p), [0.5, 0, 0, 0.5], atol=1e-5)
     vm.drop()
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_fused_brickwork_equals_per_gate_executor(pkg, dtype):
+    """Tiled multi-gate passes vs one pass per gate on the benchmark's circuit
+    family (brickwork, Haar gates, Hermitian cotangents) at n = 22, default tile
+    geometry: identical densities and gradients up to rounding."""
+    import importlib
+    bench = importlib.import_module("bench")
+    from quantum_differentiable_circuit import Circuit
+    n, depth = 22, 12
+    var, cts = bench.brickwork_inputs(n, depth, dtype)
+    out = {}
+    for fuse in (0, 1):
+        c = Circuit(n, precision=prec(dtype))
+        c.set_option("fuse", fuse)
+        bench.build_brickwork(c, n, depth)
+        dens = c.forward([], var)
+        grads = c.backward([x.conj() for x in cts], [], var)
+        out[fuse] = (dens, grads, c.last_stats()["hbm_passes"])
+    tol = TOL[np.dtype(dtype)] * 10
+    assert_close_list(out[1][0], out[0][0], tol)
+    gscale = max(np.abs(g).max() for g in out[0][1])
+    assert max(np.abs(a - b).max() for a, b in zip(out[1][1], out[0][1])) / gscale < tol
+    assert out[1][2] < out[0][2] / 3, "fusion must cut the number of HBM sweeps"

@@ -172,28 +172,36 @@ def build_autodiff_circuit(c, n, layers):
 def autodiff_gates(rng, n, layers, dtype=np.complex128):
     """Gate lists of src/test_autodiff.py:96-118 (NumPy RNG instead of JAX keys)."""
     cnot = np.array([1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 1, 0, 0, 1, 0], dtype=dtype)
-    half = (n - 1) // 2
     rc = lambda k: (rng.normal(size=k * k) + 1j * rng.normal(size=k * k))  # noqa: E731
 
-    def one_list():
+    def one_list(pairs):
+        # the file uses int((n-1)/2) for both lists, valid for its odd n = 15; for
+        # even n the variable (even-offset) and constant (odd-offset) pair counts differ
         gl = []
         for _ in range(layers):
             gl += [haar_unitary(rng, 2) for _ in range(n)]
-            gl += half * [cnot]
-            gl += [np.exp(1j * rng.normal(size=4)) for _ in range(half)]
+            gl += pairs * [cnot]
+            gl += [np.exp(1j * rng.normal(size=4)) for _ in range(pairs)]
             gl += [0.01 * rc(2) + haar_unitary(rng, 2) for _ in range(n)]
-            gl += [0.01 * rc(4) + haar_unitary(rng, 4) for _ in range(half)]
+            gl += [0.01 * rc(4) + haar_unitary(rng, 4) for _ in range(pairs)]
         return [np.asarray(g, dtype=dtype) for g in gl]
 
-    return one_list(), one_list()  # (const, var)
+    return one_list(len(range(1, n - 1, 2))), one_list(len(range(0, n - 1, 2)))  # (const, var)
+
+
+def autodiff_layout(n, layers, pairs):
+    sizes = []
+    for _ in range(layers):
+        sizes += [4] * n + [16] * pairs + [4] * pairs + [4] * n + [16] * pairs
+    return sizes
 
 
 def autodiff_var_layout(n, layers):
-    half = (n - 1) // 2
-    sizes = []
-    for _ in range(layers):
-        sizes += [4] * n + [16] * half + [4] * half + [4] * n + [16] * half
-    return sizes
+    return autodiff_layout(n, layers, len(range(0, n - 1, 2)))
+
+
+def autodiff_const_layout(n, layers):
+    return autodiff_layout(n, layers, len(range(1, n - 1, 2)))
 
 
 def tsallis_loss_and_cotangents(dens):

@@ -56,10 +56,10 @@ def test_circuit_matches_reference_replay_live(pkg, dtype, fuse):
     densities and gradients vs the reference CUDA library driven by the replay of
     src/circuit.rs (<= 1e-5 f32, <= 1e-12 f64, relative to the largest entry)."""
     from quantum_differentiable_circuit import Circuit
-    n, layers = 12, 2
+    n, layers = 13, 2
     rng = np.random.default_rng(42)
     const, var = autodiff_gates(rng, n, layers, dtype)
-    c = Circuit(n, precision=prec(dtype)); c.set_option("fuse", fuse)
+    c = Circuit(n, precision=prec(dtype)); c.set_option("fuse", fuse); c.set_option("tile_bits", 11)
     r = rr.RefCircuit(n, prec(dtype))
     build_autodiff_circuit(c, n, layers); build_autodiff_circuit(r, n, layers)
     tol = TOL[np.dtype(dtype)] * (2 if dtype == np.complex64 else 20)

@@ -1,0 +1,76 @@
+"""GPU, world_size > 1: ShardedCircuit (NCCL half-shard exchanges between GPUs of
+one box) must reproduce the single-GPU executor and the oracle.  Needs >= 2
+visible GPUs (`gpurun --gpus 2`); skipped on a single-GPU box."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _ngpus():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+def _worker(rank, world, port, case, n, precision, fuse, q):
+    import importlib
+    import torch
+    import torch.distributed as dist
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root); sys.path.insert(0, os.path.join(root, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    importlib.import_module("differentiable-quantum-circuit-cuda_b200")
+    sharded = importlib.import_module("differentiable-quantum-circuit-cuda_b200.sharded")
+    from test_scheduler import make_case, reference_results
+    dtype = np.complex64 if precision == "f32" else np.complex128
+    o, const, var = make_case(case, n, np.random.default_rng(5))
+    dens_ref, cts_conj, grads_ref = reference_results(o, const, var)
+    c = sharded.ShardedCircuit(n, precision=precision)
+    c.set_option("fuse", fuse)
+    c.set_option("tile_bits", 11)
+    for inst in o.instructions:
+        c._add(*inst)
+    cg, vg = [g.astype(dtype) for g in const], [g.astype(dtype) for g in var]
+    dens = c.forward(cg, vg)
+    grads = c.backward([x.astype(dtype) for x in cts_conj], cg, vg)
+    err_d = max(np.abs(a - b).max() for a, b in zip(dens, dens_ref))
+    scale = max(np.abs(x).max() for x in grads_ref)
+    err_g = max(np.abs(a - b).max() for a, b in zip(grads, grads_ref)) / scale
+    shard = c.get_cpu_state_copy()
+    init = np.zeros_like(shard)
+    if rank == 0:
+        init[0] = 1
+    q.put((rank, float(err_d), float(err_g), float(np.abs(shard - init).max())))
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(_ngpus() < 2, reason="needs >= 2 GPUs")
+@pytest.mark.parametrize("case", ["brickwork", "autodiff", "vqse"])
+@pytest.mark.parametrize("precision", ["f32", "f64"])
+@pytest.mark.parametrize("fuse", [0, 1])
+def test_sharded_matches_oracle(case, precision, fuse):
+    import torch.multiprocessing as mp
+    world = 2 if _ngpus() < 4 else 4
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    n = 15
+    procs = [ctx.Process(target=_worker, args=(r, world, port, case, n, precision, fuse, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=600) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    tol = 2e-4 if precision == "f32" else 1e-11
+    for rank, err_d, err_g, err_s in results:
+        assert err_d < tol and err_g < tol and err_s < tol * 10, (rank, err_d, err_g, err_s)
