@@ -66,6 +66,11 @@ __host__ __device__ __forceinline__ uint64_t ins0(uint64_t i, int pos) {
   return ((i >> pos) << (pos + 1)) | low;
 }
 
+__host__ __device__ __forceinline__ uint32_t ins0_32(uint32_t i, int pos) {
+  const uint32_t low = i & ((1u << pos) - 1u);
+  return ((i >> pos) << (pos + 1)) | low;
+}
+
 // ---- gate parameter blocks (passed by value as kernel parameters; no
 // __constant__ slots, so concurrent streams/threads do not race the way
 // src/primitives.cu:109-111 + README.md:13 do) -----------------------------

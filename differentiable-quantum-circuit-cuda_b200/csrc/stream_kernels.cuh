@@ -144,6 +144,8 @@ struct GeoQ1H {
   int pv;  // bit position in vector-index space
   __device__ __forceinline__ uint64_t base(uint64_t i) const { return ins0(i, pv); }
   __device__ __forceinline__ uint64_t off(int c) const { return (uint64_t)c << pv; }
+  __device__ __forceinline__ uint32_t base32(uint32_t i) const { return ins0_32(i, pv); }
+  __device__ __forceinline__ uint32_t off32(int c) const { return (uint32_t)c << pv; }
   static __device__ __forceinline__ void unpack(const VecU (&v)[NVEC], cplx_t (&a)[NG][K]) {
 #pragma unroll
     for (int e = 0; e < NG; e++)
@@ -172,6 +174,10 @@ struct GeoQ2HH {
   __device__ __forceinline__ uint64_t off(int c) const {
     return ((uint64_t)(c >> 1) << hv) + ((uint64_t)(c & 1) << lv);
   }
+  __device__ __forceinline__ uint32_t base32(uint32_t i) const { return ins0_32(ins0_32(i, lv), hv); }
+  __device__ __forceinline__ uint32_t off32(int c) const {
+    return ((uint32_t)(c >> 1) << hv) + ((uint32_t)(c & 1) << lv);
+  }
   static __device__ __forceinline__ void unpack(const VecU (&v)[NVEC], cplx_t (&a)[NG][K]) {
 #pragma unroll
     for (int e = 0; e < NG; e++)
@@ -198,6 +204,8 @@ struct GeoQ1L {
   static constexpr int NVEC = 1, NG = 1, K = 2;
   __device__ __forceinline__ uint64_t base(uint64_t i) const { return i; }
   __device__ __forceinline__ uint64_t off(int) const { return 0; }
+  __device__ __forceinline__ uint32_t base32(uint32_t i) const { return i; }
+  __device__ __forceinline__ uint32_t off32(int) const { return 0; }
   static __device__ __forceinline__ void unpack(const VecU (&v)[NVEC], cplx_t (&a)[NG][K]) {
     a[0][0].x = v[0].r[0];
     a[0][0].y = v[0].r[1];
@@ -218,6 +226,8 @@ struct GeoQ2LH {
   int hv;  // hi - 1
   __device__ __forceinline__ uint64_t base(uint64_t i) const { return ins0(i, hv); }
   __device__ __forceinline__ uint64_t off(int c) const { return (uint64_t)c << hv; }
+  __device__ __forceinline__ uint32_t base32(uint32_t i) const { return ins0_32(i, hv); }
+  __device__ __forceinline__ uint32_t off32(int c) const { return (uint32_t)c << hv; }
   static __device__ __forceinline__ void unpack(const VecU (&v)[NVEC], cplx_t (&a)[NG][K]) {
 #pragma unroll
     for (int h = 0; h < 2; h++)

@@ -87,31 +87,45 @@ struct TileBwdParams {
 };
 
 // ------------------------------------------------------------ tile <-> HBM
+// Per-thread addressing of a tile, computed ONCE per kernel: vector v = tid +
+// i * NT of the tile lives at  tile_base + lo + it[i]  (in vec_t units), where
+// `lo` depends on the thread only and `it[i]` on the iteration only (the run
+// index splits into disjoint thread / iteration bits).
+template <int NT>
+struct TileAddr {
+  static constexpr int MAXI = 16;  // nvec / NT for the largest supported tile
+  uint64_t lo;
+  uint32_t it[MAXI];  // in units of runs (2^(L - LV) vectors): fits 32 bits for n <= 34
+  int niter, runv_log;
+  __device__ __forceinline__ void init(const TileGeo& geo) {
+    const int nvec = 1 << (geo.T - QDC_LV);
+    runv_log = geo.L - QDC_LV;
+    const int tid = threadIdx.x;
+    niter = nvec / NT;
+    lo = (geo.hi((uint64_t)(tid >> runv_log)) >> QDC_LV) + (uint64_t)(tid & ((1 << runv_log) - 1));
+#pragma unroll
+    for (int i = 0; i < MAXI; i++)
+      it[i] = (i < niter) ? (uint32_t)(geo.hi((uint64_t)i * (NT >> runv_log)) >> geo.L) : 0u;
+  }
+};
+
 template <int NT, bool LOAD>
-__device__ __forceinline__ void tile_io(vec_t* __restrict__ gmem, vec_t* __restrict__ smv, const TileGeo& geo,
-                                        uint64_t tile) {
-  const int nvec = 1 << (geo.T - QDC_LV);
-  const int runv_log = geo.L - QDC_LV;
-  const uint64_t base = geo.tile(tile) >> QDC_LV;
+__device__ __forceinline__ void tile_io(vec_t* __restrict__ gmem, vec_t* __restrict__ smv, const TileAddr<NT>& ta,
+                                        uint64_t tile_base_vec) {
+  const uint64_t base = tile_base_vec + ta.lo;
   const int tid = threadIdx.x;
-  // v = tid + i * NT; run index r = v >> runv_log splits into disjoint thread / iteration bits
-  const uint64_t off_lo = (geo.hi((uint64_t)(tid >> runv_log)) >> QDC_LV) + (uint64_t)(tid & ((1 << runv_log) - 1));
   constexpr int UNR = 4;
-  for (int i0 = 0; i0 < nvec / NT; i0 += UNR) {
-    vec_t tmp[UNR];
-    uint64_t g[UNR];
 #pragma unroll
-    for (int u = 0; u < UNR; u++) {
-      const int i = i0 + u;
-      g[u] = base + off_lo + (geo.hi((uint64_t)i * (NT >> runv_log)) >> QDC_LV);
-      if (LOAD && i < nvec / NT) tmp[u] = gmem[g[u]];
-    }
+  for (int i0 = 0; i0 < TileAddr<NT>::MAXI; i0 += UNR) {
+    if (i0 < ta.niter) {
+      vec_t tmp[UNR];
 #pragma unroll
-    for (int u = 0; u < UNR; u++) {
-      const int i = i0 + u;
-      if (i < nvec / NT) {
-        const int v = tid + i * NT;
-        if (LOAD) smv[v] = tmp[u]; else gmem[g[u]] = smv[v];
+      for (int u = 0; u < UNR; u++)
+        if (LOAD) tmp[u] = gmem[base + ((uint64_t)ta.it[i0 + u] << ta.runv_log)];
+#pragma unroll
+      for (int u = 0; u < UNR; u++) {
+        const int v = tid + (i0 + u) * NT;
+        if (LOAD) smv[v] = tmp[u]; else gmem[base + ((uint64_t)ta.it[i0 + u] << ta.runv_log)] = smv[v];
       }
     }
   }
@@ -138,16 +152,16 @@ __device__ __forceinline__ void tile_apply(vec_t* smv, const Geo& geo, int nitem
   constexpr int K = Geo::K;
   for (int i = threadIdx.x; i < nitems; i += NT) {
     VecU v[Geo::NVEC];
-    const uint32_t base = (uint32_t)geo.base((uint64_t)i);
+    const uint32_t base = geo.base32((uint32_t)i);
 #pragma unroll
-    for (int c = 0; c < Geo::NVEC; c++) v[c].v = smv[base + (uint32_t)geo.off(c)];
+    for (int c = 0; c < Geo::NVEC; c++) v[c].v = smv[base + geo.off32(c)];
     cplx_t a[Geo::NG][K];
     Geo::unpack(v, a);
 #pragma unroll
     for (int e = 0; e < Geo::NG; e++) mv<K>(G.re, G.im, a[e]);
     Geo::pack(v, a);
 #pragma unroll
-    for (int c = 0; c < Geo::NVEC; c++) smv[base + (uint32_t)geo.off(c)] = v[c].v;
+    for (int c = 0; c < Geo::NVEC; c++) smv[base + geo.off32(c)] = v[c].v;
   }
 }
 
@@ -175,8 +189,11 @@ __global__ void __launch_bounds__(QDC_TILE_NT_F, 3)
   extern __shared__ __align__(16) unsigned char tile_smem[];
   vec_t* smv = (vec_t*)tile_smem;
   const int nvec = 1 << (p.geo.T - QDC_LV);
+  TileAddr<QDC_TILE_NT_F> ta;
+  ta.init(p.geo);
   for (uint64_t tile = blockIdx.x; tile < p.geo.ntiles; tile += gridDim.x) {
-    tile_io<QDC_TILE_NT_F, true>((vec_t*)state, smv, p.geo, tile);
+    const uint64_t tbase = p.geo.tile(tile) >> QDC_LV;
+    tile_io<QDC_TILE_NT_F, true>((vec_t*)state, smv, ta, tbase);
     __syncthreads();
     for (int g = 0; g < p.ngates; g++) {
       const TileGateF& G = p.g[g];
@@ -211,7 +228,7 @@ __global__ void __launch_bounds__(QDC_TILE_NT_F, 3)
       }
       __syncthreads();
     }
-    tile_io<QDC_TILE_NT_F, false>((vec_t*)state, smv, p.geo, tile);
+    tile_io<QDC_TILE_NT_F, false>((vec_t*)state, smv, ta, tbase);
     __syncthreads();
   }
 }
@@ -226,25 +243,25 @@ __device__ __forceinline__ void tile_rev(vec_t* smf, vec_t* smb, const Geo& geo,
   // gate matrix live at a time (register pressure).
   for (int i = threadIdx.x; i < nitems; i += NT) {
     VecU vf[Geo::NVEC];
-    const uint32_t base = (uint32_t)geo.base((uint64_t)i);
+    const uint32_t base = geo.base32((uint32_t)i);
 #pragma unroll
-    for (int c = 0; c < Geo::NVEC; c++) vf[c].v = smf[base + (uint32_t)geo.off(c)];
+    for (int c = 0; c < Geo::NVEC; c++) vf[c].v = smf[base + geo.off32(c)];
     cplx_t a[Geo::NG][K];
     Geo::unpack(vf, a);
 #pragma unroll
     for (int e = 0; e < Geo::NG; e++) mv<K>(G.ire, G.iim, a[e]);
     Geo::pack(vf, a);
 #pragma unroll
-    for (int c = 0; c < Geo::NVEC; c++) smf[base + (uint32_t)geo.off(c)] = vf[c].v;
+    for (int c = 0; c < Geo::NVEC; c++) smf[base + geo.off32(c)] = vf[c].v;
   }
   // phase B: gradient from (pre-gate state, post-gate adjoint), then pull the adjoint back
   for (int i = threadIdx.x; i < nitems; i += NT) {
     VecU vf[Geo::NVEC], vb[Geo::NVEC];
-    const uint32_t base = (uint32_t)geo.base((uint64_t)i);
+    const uint32_t base = geo.base32((uint32_t)i);
 #pragma unroll
     for (int c = 0; c < Geo::NVEC; c++) {
-      vb[c].v = smb[base + (uint32_t)geo.off(c)];
-      if (G.slot >= 0) vf[c].v = smf[base + (uint32_t)geo.off(c)];
+      vb[c].v = smb[base + geo.off32(c)];
+      if (G.slot >= 0) vf[c].v = smf[base + geo.off32(c)];
     }
     cplx_t b[Geo::NG][K];
     Geo::unpack(vb, b);
@@ -258,7 +275,7 @@ __device__ __forceinline__ void tile_rev(vec_t* smf, vec_t* smb, const Geo& geo,
     for (int e = 0; e < Geo::NG; e++) mv<K>(G.tre, G.tim, b[e]);
     Geo::pack(vb, b);
 #pragma unroll
-    for (int c = 0; c < Geo::NVEC; c++) smb[base + (uint32_t)geo.off(c)] = vb[c].v;
+    for (int c = 0; c < Geo::NVEC; c++) smb[base + geo.off32(c)] = vb[c].v;
   }
 }
 
@@ -309,9 +326,12 @@ __global__ void __launch_bounds__(QDC_TILE_NT_B, 3)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int i = threadIdx.x; i < QDC_TILE_MAXG_B * 32; i += QDC_TILE_NT_B) sm_acc[i] = 0.0;
   __syncthreads();
+  TileAddr<QDC_TILE_NT_B> ta;
+  ta.init(p.geo);
   for (uint64_t tile = blockIdx.x; tile < p.geo.ntiles; tile += gridDim.x) {
-    tile_io<QDC_TILE_NT_B, true>((vec_t*)fwd, smf, p.geo, tile);
-    tile_io<QDC_TILE_NT_B, true>((vec_t*)bwd, smb, p.geo, tile);
+    const uint64_t tbase = p.geo.tile(tile) >> QDC_LV;
+    tile_io<QDC_TILE_NT_B, true>((vec_t*)fwd, smf, ta, tbase);
+    tile_io<QDC_TILE_NT_B, true>((vec_t*)bwd, smb, ta, tbase);
     __syncthreads();
     for (int g = 0; g < p.ngates; g++) {
       const TileGateB& G = p.g[g];
@@ -361,8 +381,8 @@ __global__ void __launch_bounds__(QDC_TILE_NT_B, 3)
         sm_acc[g * 32 + lane] += s;
       }
     }
-    tile_io<QDC_TILE_NT_B, false>((vec_t*)fwd, smf, p.geo, tile);
-    tile_io<QDC_TILE_NT_B, false>((vec_t*)bwd, smb, p.geo, tile);
+    tile_io<QDC_TILE_NT_B, false>((vec_t*)fwd, smf, ta, tbase);
+    tile_io<QDC_TILE_NT_B, false>((vec_t*)bwd, smb, ta, tbase);
     __syncthreads();
   }
   for (int i = threadIdx.x; i < p.ngates * 32; i += QDC_TILE_NT_B)
@@ -398,6 +418,7 @@ static inline const char* make_tile_geo(const qdc::Plan& plan, const qdc::Step& 
   }
   std::sort(bits.begin(), bits.end());
   if (T < min_T) return qdc_errf("register too small for a tiled pass.");
+  if (T - QDC_LV > 11) return qdc_errf("tile_bits too large: at most %d.", 11 + QDC_LV);
   int L = 0;
   while (L < T && bits[L] == L) L++;
   if (L < low_bits && L < T) return qdc_errf("tile does not contain the low bits.");
