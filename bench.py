@@ -234,7 +234,12 @@ def run_ours(args):
         t = torch.tensor([dev_ms, wall], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dev_ms, wall = float(t[0]), float(t[1])
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
     if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
         return
     peaks = {}
     try:
@@ -280,6 +285,8 @@ def run_ours(args):
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(n_total)
     print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def run_reference(args):
