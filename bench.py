@@ -270,7 +270,7 @@ def run_ours(args):
                    "local_qubits": args.qubits, "depth": args.depth, "gates": n_gates, "densities": n_dens,
                    "state_bytes_per_gpu": int(np.dtype(dtype).itemsize) << args.qubits,
                    "l2": "inputs (state + adjoint) far larger than L2; no flush needed",
-                   "executor": "fused tiled passes" if args.fuse else "one pass per gate"},
+                   "executor": ["one pass per gate", "tiled multi-gate passes", "register-blocked tiled passes"][args.fuse]},
         "effective_hbm_gbs": round(total_alg * world / (dev_ms * 1e-3) / 1e9, 1),
         "effective_hbm_frac": round(total_alg / (dev_ms * 1e-3) / 1e9 / peak, 4),
         "roofline": roofline,
@@ -351,7 +351,7 @@ def main():
     ap.add_argument("--depth", type=int, default=100)
     ap.add_argument("--ref-depth", type=int, default=2, help="depth of the bounded sample the reference arm runs")
     ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
-    ap.add_argument("--fuse", type=int, default=1)
+    ap.add_argument("--fuse", type=int, default=2, help="0: one pass per gate, 1: tiled passes, 2: register-blocked tiled passes")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

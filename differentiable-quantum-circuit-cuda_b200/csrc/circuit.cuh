@@ -374,6 +374,7 @@ class Circuit {
     plan_all_dens_ = all_dens;
     exec_p2_.assign(insts_.size(), -1);
     exec_p1_.assign(insts_.size(), -1);
+    diag_hilo_.assign(insts_.size(), 0);
     auto note = [&](const qdc::Step& st) {
       if (st.inst >= 0) {
         exec_p2_[st.inst] = st.p2;
@@ -561,7 +562,8 @@ class Circuit {
           QDC_TRY(fwd_gate_step(st, gp));
           break;
         case qdc::ST_TILE:
-          QDC_TRY(run_tile_forward(st, gp));
+          if (opt_fuse_ >= 2) QDC_TRY(run_tile_forward_rb(st, gp, false));
+          else QDC_TRY(run_tile_forward(st, gp));
           break;
         case qdc::ST_SWAP:
           PROF(CAT_EXCHANGE, 0, exchange(state_, st.gbit, st.lpos));
@@ -643,6 +645,7 @@ class Circuit {
       } else if (kind_is_diag(in.kind)) {
         zc m[4];
         scatter_diag_grad(h, exec_p2_[i], exec_p1_[i], m);
+        if (diag_hilo_[i]) std::swap(m[1], m[2]);
         for (int j = 0; j < 4; j++) {
           out[o + j].x = (real_t)m[j].real();
           out[o + j].y = (real_t)m[j].imag();
@@ -719,7 +722,18 @@ class Circuit {
           QDC_TRY(bwd_gate_step(st, gp, vslot, live));
           break;
         case qdc::ST_TILE:
-          QDC_TRY(run_tile_backward(st, gp, vslot, live));
+          if (opt_fuse_ >= 2) {
+#ifdef QDC_F64
+            // f64: 2 x 16 double-complex amplitudes + 32 double accumulators do not fit the
+            // register file without spilling; the reverse pass keeps the per-gate tile kernel.
+            if (live) QDC_TRY(run_tile_backward(st, gp, vslot, live));
+#else
+            if (live) QDC_TRY(run_tile_backward_rb(st, gp, vslot));
+#endif
+            else QDC_TRY(run_tile_forward_rb(st, gp, true));
+          } else {
+            QDC_TRY(run_tile_backward(st, gp, vslot, live));
+          }
           break;
         case qdc::ST_SWAP:
           PROF(CAT_EXCHANGE, 0, exchange(state_, st.gbit, st.lpos));
@@ -735,7 +749,11 @@ class Circuit {
   const char* run_tile_forward(const qdc::Step& t, const std::vector<const cplx_t*>& gp);
   const char* run_tile_backward(const qdc::Step& t, const std::vector<const cplx_t*>& gp,
                                 const std::vector<long>& vslot, bool live);
+  const char* run_tile_forward_rb(const qdc::Step& t, const std::vector<const cplx_t*>& gp, bool uncompute);
+  const char* run_tile_backward_rb(const qdc::Step& t, const std::vector<const cplx_t*>& gp,
+                                   const std::vector<long>& vslot);
   void release_tiles();
+  std::vector<char> diag_hilo_;  // diagonal gradient of this instruction came back in (hi,lo) order
   double* tile_partials_ = nullptr;
   size_t tile_partials_cap_ = 0;
 };

@@ -3,7 +3,7 @@
 // Exports: the 18 legacy symbols (include/qdc_primitives.h) and the circuit
 // ABI (include/qdc_circuit.h).  Everything else has hidden visibility.
 #include "primitives_abi.cuh"
-#include "tile_kernels.cuh"
+#include "tile_rb_kernels.cuh"
 
 struct qdc_circuit {
   Circuit impl;

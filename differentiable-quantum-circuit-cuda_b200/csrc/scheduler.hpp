@@ -39,12 +39,22 @@ struct Step {
   int gbit = -1, lpos = -1;  // SWAP: global bit index (physical position n_loc + gbit) <-> local position
   int first = 0, count = 0;  // TILE: range in Plan::tile_steps
   int tb_first = 0, tb_count = 0;  // TILE: range in Plan::tile_bits (sorted physical positions)
+  int grp_first = 0, grp_count = 0;  // TILE: range in Plan::groups (register-block groups)
+};
+
+// A register-block group inside a tile pass: `count` consecutive tile gates
+// (starting at Plan::tile_steps[first]) that all act within <= 4 positions.
+struct Group {
+  int first = 0, count = 0;
+  int nbits = 0;
+  int bits[4] = {-1, -1, -1, -1};  // physical positions, ascending
 };
 
 struct Plan {
   std::vector<Step> steps;
   std::vector<Step> tile_steps;   // GATE steps belonging to TILE passes
   std::vector<int> tile_bits;
+  std::vector<Group> groups;
   std::vector<int> final_map;     // logical qubit -> physical position after the plan
 };
 
@@ -61,6 +71,7 @@ struct SchedOptions {
   int low_bits = 0;  // L: low physical positions forced into every tile
   int min_tile_gates = 2;  // a tile pass must hold at least this many gates to beat streaming
   int max_tile_gates = 24; // capacity of the backward tile kernel's parameter block
+  int group_bits = 4;      // register-block width: gates of a pass are grouped by <= this many positions
 };
 
 class Scheduler {
@@ -207,7 +218,9 @@ class Scheduler {
         t.type = ST_TILE;
         t.first = (int)plan.tile_steps.size();
         t.count = (int)in_tile.size();
-        for (const Step& st : in_tile) plan.tile_steps.push_back(st);
+        t.grp_first = (int)plan.groups.size();
+        group_tile(plan, in_tile);  // appends the gates to plan.tile_steps in group order
+        t.grp_count = (int)plan.groups.size() - t.grp_first;
         std::sort(bits.begin(), bits.end());
         t.tb_first = (int)plan.tile_bits.size();
         for (int l = 0; l < o_.low_bits; l++) plan.tile_bits.push_back(l);
@@ -217,6 +230,49 @@ class Scheduler {
       } else {
         for (const Step& st : in_tile) plan.steps.push_back(st);
       }
+      pending.swap(deferred);
+    }
+  }
+
+  // Second-level grouping for register blocking: partition the gates of one
+  // tile pass (in dependency order) into groups acting within <= group_bits
+  // positions, deferring what does not fit together with its dependants.
+  void group_tile(Plan& plan, const std::vector<Step>& gates) {
+    std::vector<Step> pending(gates.begin(), gates.end());
+    const int RB = o_.group_bits < 2 ? 2 : (o_.group_bits > 4 ? 4 : o_.group_bits);
+    while (!pending.empty()) {
+      std::vector<int> bits;
+      std::vector<Step> grp, deferred;
+      std::vector<bool> dirty(o_.n, false);
+      for (const Step& st : pending) {
+        const bool dep = dirty[st.p2] || (st.p1 >= 0 && dirty[st.p1]);
+        bool fits = false;
+        if (!dep) {
+          int extra = 0;
+          if (std::find(bits.begin(), bits.end(), st.p2) == bits.end()) extra++;
+          if (st.p1 >= 0 && st.p1 != st.p2 && std::find(bits.begin(), bits.end(), st.p1) == bits.end()) extra++;
+          if ((int)bits.size() + extra <= RB) {
+            fits = true;
+            if (std::find(bits.begin(), bits.end(), st.p2) == bits.end()) bits.push_back(st.p2);
+            if (st.p1 >= 0 && std::find(bits.begin(), bits.end(), st.p1) == bits.end()) bits.push_back(st.p1);
+          }
+        }
+        if (fits) {
+          grp.push_back(st);
+        } else {
+          deferred.push_back(st);
+          dirty[st.p2] = true;
+          if (st.p1 >= 0) dirty[st.p1] = true;
+        }
+      }
+      Group g;
+      g.first = (int)plan.tile_steps.size();
+      g.count = (int)grp.size();
+      std::sort(bits.begin(), bits.end());
+      g.nbits = (int)bits.size();
+      for (int k = 0; k < g.nbits; k++) g.bits[k] = bits[k];
+      for (const Step& st : grp) plan.tile_steps.push_back(st);
+      plan.groups.push_back(g);
       pending.swap(deferred);
     }
   }

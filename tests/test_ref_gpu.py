@@ -50,7 +50,7 @@ def test_primitives_match_reference_library_live(pkg, dtype):
 
 @needs_ref
 @pytest.mark.parametrize("dtype", DTYPES)
-@pytest.mark.parametrize("fuse", [0, 1])
+@pytest.mark.parametrize("fuse", [0, 1, 2])
 def test_circuit_matches_reference_replay_live(pkg, dtype, fuse):
     """BASELINE.json configs[1] shape: layered circuit with every instruction kind;
     densities and gradients vs the reference CUDA library driven by the replay of

@@ -56,7 +56,7 @@ def _worker(rank, world, port, case, n, precision, fuse, q):
 @pytest.mark.skipif(_ngpus() < 2, reason="needs >= 2 GPUs")
 @pytest.mark.parametrize("case", ["brickwork", "autodiff", "vqse"])
 @pytest.mark.parametrize("precision", ["f32", "f64"])
-@pytest.mark.parametrize("fuse", [0, 1])
+@pytest.mark.parametrize("fuse", [0, 1, 2])
 def test_sharded_matches_oracle(case, precision, fuse):
     import torch.multiprocessing as mp
     world = 2 if _ngpus() < 4 else 4
