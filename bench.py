@@ -186,6 +186,14 @@ def run_ours(args):
         circ = pkg.Circuit(n_total, precision=args.precision)
     circ.set_option("fuse", args.fuse)
     circ.set_option("profile", 1)
+    if args.tile_bits:
+        circ.set_option("tile_bits", args.tile_bits)
+    if args.low_bits:
+        circ.set_option("low_bits", args.low_bits)
+    if args.max_tile_gates:
+        circ.set_option("max_tile_gates", args.max_tile_gates)
+    if args.tile_debug:
+        circ.set_option("tile_debug", args.tile_debug)
     n_gates, n_dens = build_brickwork(circ, n_total, args.depth)
     var, cts = brickwork_inputs(n_total, args.depth, dtype)
     cts_conj = [c.conj() for c in cts]
@@ -352,6 +360,10 @@ def main():
     ap.add_argument("--ref-depth", type=int, default=2, help="depth of the bounded sample the reference arm runs")
     ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
     ap.add_argument("--fuse", type=int, default=2, help="0: one pass per gate, 1: tiled passes, 2: register-blocked tiled passes")
+    ap.add_argument("--tile-bits", type=int, default=0, help="T of the tiled passes (0: library default)")
+    ap.add_argument("--low-bits", type=int, default=0, help="L lowest positions forced into every tile (0: default)")
+    ap.add_argument("--max-tile-gates", type=int, default=0)
+    ap.add_argument("--tile-debug", type=int, default=0, help="profiling aid (1: no HBM traffic, 2: no gates); invalid results")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -723,13 +723,14 @@ class Circuit {
           break;
         case qdc::ST_TILE:
           if (opt_fuse_ >= 2) {
-#ifdef QDC_F64
-            // f64: 2 x 16 double-complex amplitudes + 32 double accumulators do not fit the
-            // register file without spilling; the reverse pass keeps the per-gate tile kernel.
-            if (live) QDC_TRY(run_tile_backward(st, gp, vslot, live));
-#else
-            if (live) QDC_TRY(run_tile_backward_rb(st, gp, vslot));
+            // The register-blocked reverse kernel (2 x 16 amplitudes + 32 accumulators per thread)
+            // is occupancy-starved and measured slower than the per-gate tile kernel (fuse = 3
+            // selects it for experiments); the reverse pass keeps the per-gate tile kernel.
+#ifndef QDC_F64
+            if (live && opt_fuse_ >= 3) QDC_TRY(run_tile_backward_rb(st, gp, vslot));
+            else
 #endif
+            if (live) QDC_TRY(run_tile_backward(st, gp, vslot, live));
             else QDC_TRY(run_tile_forward_rb(st, gp, true));
           } else {
             QDC_TRY(run_tile_backward(st, gp, vslot, live));

@@ -117,6 +117,7 @@ QDC_EXPORT const char* qdc_circuit_set_option(qdc_circuit* c, const char* key, l
   else if (strcmp(key, "profile") == 0) c->impl.prof_.on = value != 0;
   else if (strcmp(key, "tile_bits") == 0) c->impl.opt_tile_bits_ = (int)value;
   else if (strcmp(key, "low_bits") == 0) c->impl.opt_low_bits_ = (int)value;
+  else if (strcmp(key, "tile_debug") == 0) g_tile_debug = (int)value;  // profiling aid, results invalid when != 0
   else if (strcmp(key, "max_tile_gates") == 0) {
     if (value < 1 || value > QDC_TILE_MAXG_B) return qdc_errf("max_tile_gates must be in 1..%d.", QDC_TILE_MAXG_B);
     c->impl.opt_max_tile_gates_ = (int)value;

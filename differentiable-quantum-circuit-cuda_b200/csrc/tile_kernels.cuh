@@ -20,7 +20,7 @@
 #pragma once
 #include "circuit.cuh"
 
-#define QDC_TILE_NT_F 256  // threads per CTA, forward tile kernel (3 CTAs / SM)
+#define QDC_TILE_NT_F 128  // threads per CTA, forward tile kernel (6 CTAs / SM: more independent barrier domains)
 #define QDC_TILE_NT_B 128  // backward tile kernel: fewer threads, more registers each (3 CTAs / SM)
 
 #ifdef QDC_F64
@@ -63,17 +63,71 @@ struct TileGeo {
   BitDeposit hi;    // run index within the tile (T-L bits) -> amplitude offset
   BitDeposit tile;  // tile number (n-T bits)               -> amplitude base
   uint64_t ntiles;
+  int debug;  // profiling aid: 1 = skip HBM traffic, 2 = skip the gates (results are then wrong)
 };
 
 enum { TG_Q1 = 0, TG_Q2 = 1, TG_DIAG = 2 };
 
+// Gate matrix as the tile kernels consume it.  f32: pre-packed for the packed
+// FP32 FMA of sm_100 (FFMA2, `fma.rn.f32x2`): A = (re, re), B = (-im, im), so
+// that one complex multiply-accumulate o += g * a is two FFMA2
+//   o = fma2(A, (a.x, a.y), o);  o = fma2(B, (a.y, a.x), o)
+// i.e. half the issue slots of four scalar FFMAs (same pipe throughput,
+// profiles/microbench/ffma2_bench.cu) -- the freed slots absorb the LDS / LDC /
+// integer instructions that made the scalar version issue-bound.
+#ifdef QDC_F64
+struct GateMat {
+  real_t re[16], im[16];
+};
+__host__ __device__ __forceinline__ real_t gm_re(const GateMat& m, int j) { return m.re[j]; }
+__host__ __device__ __forceinline__ real_t gm_im(const GateMat& m, int j) { return m.im[j]; }
+static inline void gm_fill(GateMat& m, const real_t* re, const real_t* im) {
+  for (int i = 0; i < 16; i++) {
+    m.re[i] = re[i];
+    m.im[i] = im[i];
+  }
+}
+#else
+struct GateMat {
+  float2 A[16], B[16];
+};
+__host__ __device__ __forceinline__ real_t gm_re(const GateMat& m, int j) { return m.A[j].x; }
+__host__ __device__ __forceinline__ real_t gm_im(const GateMat& m, int j) { return m.B[j].y; }
+static inline void gm_fill(GateMat& m, const real_t* re, const real_t* im) {
+  for (int i = 0; i < 16; i++) {
+    m.A[i] = make_float2(re[i], re[i]);
+    m.B[i] = make_float2(-im[i], im[i]);
+  }
+}
+__device__ __forceinline__ float2 ffma2(const float2 a, const float2 b, const float2 c) {
+  unsigned long long ra = *reinterpret_cast<const unsigned long long*>(&a),
+                     rb = *reinterpret_cast<const unsigned long long*>(&b),
+                     rc = *reinterpret_cast<const unsigned long long*>(&c), rd;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  return *reinterpret_cast<float2*>(&rd);
+}
+__device__ __forceinline__ float2 fmul2(const float2 a, const float2 b) {
+  unsigned long long ra = *reinterpret_cast<const unsigned long long*>(&a),
+                     rb = *reinterpret_cast<const unsigned long long*>(&b), rd;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  return *reinterpret_cast<float2*>(&rd);
+}
+#endif
+
+__device__ __forceinline__ real_t gm_sel4_re(const GateMat& m, int j) {
+  return (j & 2) ? ((j & 1) ? gm_re(m, 3) : gm_re(m, 2)) : ((j & 1) ? gm_re(m, 1) : gm_re(m, 0));
+}
+__device__ __forceinline__ real_t gm_sel4_im(const GateMat& m, int j) {
+  return (j & 2) ? ((j & 1) ? gm_im(m, 3) : gm_im(m, 2)) : ((j & 1) ? gm_im(m, 1) : gm_im(m, 0));
+}
+
 struct TileGateF {  // one matrix
   int type, a, b, pad;  // tile-local bits; q2: a > b and the matrix is in (a,b) order; diag: j = 2 bit(a) + bit(b)
-  real_t re[16], im[16];
+  GateMat m;
 };
 struct TileGateB {  // inverse (for the state) and transpose (for the adjoint)
   int type, a, b, slot;  // slot < 0: constant gate (no gradient)
-  real_t ire[16], iim[16], tre[16], tim[16];
+  GateMat inv, tr;
 };
 struct TileFwdParams {
   TileGeo geo;
@@ -133,24 +187,67 @@ __device__ __forceinline__ void tile_io(vec_t* __restrict__ gmem, vec_t* __restr
 
 // ------------------------------------------------- in-tile gate application
 template <int K>
-__device__ __forceinline__ void mv(const real_t (&gre)[16], const real_t (&gim)[16], cplx_t (&a)[K]) {
+__device__ __forceinline__ void mv(const GateMat& G, cplx_t (&a)[K]) {
+#ifdef QDC_F64
   cplx_t o[K];
 #pragma unroll
   for (int r = 0; r < K; r++) {
     o[r].x = 0;
     o[r].y = 0;
 #pragma unroll
-    for (int c = 0; c < K; c++) cmac(o[r], gre[r * K + c], gim[r * K + c], a[c]);
+    for (int c = 0; c < K; c++) cmac(o[r], G.re[r * K + c], G.im[r * K + c], a[c]);
   }
 #pragma unroll
   for (int r = 0; r < K; r++) a[r] = o[r];
+#else
+  float2 as[K], o[K];
+#pragma unroll
+  for (int c = 0; c < K; c++) as[c] = make_float2(a[c].y, a[c].x);
+#pragma unroll
+  for (int r = 0; r < K; r++) {
+    o[r] = fmul2(G.A[r * K], a[0]);
+    o[r] = ffma2(G.B[r * K], as[0], o[r]);
+#pragma unroll
+    for (int c = 1; c < K; c++) {
+      o[r] = ffma2(G.A[r * K + c], a[c], o[r]);
+      o[r] = ffma2(G.B[r * K + c], as[c], o[r]);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < K; r++) a[r] = o[r];
+#endif
+}
+
+// acc[2(pK+q)] += b[p] * a[q] (no conjugation), packed on f32
+template <int K>
+__device__ __forceinline__ void outer_tile(const cplx_t (&b)[K], const cplx_t (&a)[K], real_t* acc) {
+#ifdef QDC_F64
+  outer_acc<K>(b, a, acc);
+#else
+  float2 as[K];
+#pragma unroll
+  for (int q = 0; q < K; q++) as[q] = make_float2(a[q].y, a[q].x);
+#pragma unroll
+  for (int p = 0; p < K; p++) {
+    const float2 bb = make_float2(b[p].x, b[p].x), bn = make_float2(-b[p].y, b[p].y);
+#pragma unroll
+    for (int q = 0; q < K; q++) {
+      float2 t = make_float2(acc[2 * (p * K + q)], acc[2 * (p * K + q) + 1]);
+      t = ffma2(bb, a[q], t);
+      t = ffma2(bn, as[q], t);
+      acc[2 * (p * K + q)] = t.x;
+      acc[2 * (p * K + q) + 1] = t.y;
+    }
+  }
+#endif
 }
 
 // forward: a <- G a over every item of geometry Geo in the shared tile
 template <int NT, class Geo>
 __device__ __forceinline__ void tile_apply(vec_t* smv, const Geo& geo, int nitems, const TileGateF& G) {
   constexpr int K = Geo::K;
-  for (int i = threadIdx.x; i < nitems; i += NT) {
+  for (int i0 = 0; i0 < nitems; i0 += NT) {  // uniform trip count (nitems % NT == 0): convergent loop
+    const int i = i0 + threadIdx.x;
     VecU v[Geo::NVEC];
     const uint32_t base = geo.base32((uint32_t)i);
 #pragma unroll
@@ -158,7 +255,7 @@ __device__ __forceinline__ void tile_apply(vec_t* smv, const Geo& geo, int nitem
     cplx_t a[Geo::NG][K];
     Geo::unpack(v, a);
 #pragma unroll
-    for (int e = 0; e < Geo::NG; e++) mv<K>(G.re, G.im, a[e]);
+    for (int e = 0; e < Geo::NG; e++) mv<K>(G.m, a[e]);
     Geo::pack(v, a);
 #pragma unroll
     for (int c = 0; c < Geo::NVEC; c++) smv[base + geo.off32(c)] = v[c].v;
@@ -166,16 +263,16 @@ __device__ __forceinline__ void tile_apply(vec_t* smv, const Geo& geo, int nitem
 }
 
 template <int NT>
-__device__ __forceinline__ void tile_diag(vec_t* smv, int nvec, const real_t (&dre)[16], const real_t (&dim)[16],
-                                          int a, int b) {
-  for (int i = threadIdx.x; i < nvec; i += NT) {
+__device__ __forceinline__ void tile_diag(vec_t* smv, int nvec, const GateMat& D, int a, int b) {
+  for (int i0 = 0; i0 < nvec; i0 += NT) {  // uniform trip count
+    const int i = i0 + threadIdx.x;
     VecU v;
     v.v = smv[i];
 #pragma unroll
     for (int e = 0; e < QDC_VA; e++) {
       const int amp = i * QDC_VA + e;
       const int j = 2 * ((amp >> a) & 1) + ((amp >> b) & 1);
-      const real_t dr = sel4(dre, j), di = sel4(dim, j);
+      const real_t dr = gm_sel4_re(D, j), di = gm_sel4_im(D, j);
       const real_t x = v.r[2 * e] * dr - v.r[2 * e + 1] * di, y = v.r[2 * e] * di + v.r[2 * e + 1] * dr;
       v.r[2 * e] = x;
       v.r[2 * e + 1] = y;
@@ -184,7 +281,7 @@ __device__ __forceinline__ void tile_diag(vec_t* smv, int nvec, const real_t (&d
   }
 }
 
-__global__ void __launch_bounds__(QDC_TILE_NT_F, 3)
+__global__ void __launch_bounds__(QDC_TILE_NT_F, 6)
     k_tile_fwd(cplx_t* __restrict__ state, const __grid_constant__ TileFwdParams p) {
   extern __shared__ __align__(16) unsigned char tile_smem[];
   vec_t* smv = (vec_t*)tile_smem;
@@ -193,9 +290,9 @@ __global__ void __launch_bounds__(QDC_TILE_NT_F, 3)
   ta.init(p.geo);
   for (uint64_t tile = blockIdx.x; tile < p.geo.ntiles; tile += gridDim.x) {
     const uint64_t tbase = p.geo.tile(tile) >> QDC_LV;
-    tile_io<QDC_TILE_NT_F, true>((vec_t*)state, smv, ta, tbase);
+    if (p.geo.debug != 1) tile_io<QDC_TILE_NT_F, true>((vec_t*)state, smv, ta, tbase);
     __syncthreads();
-    for (int g = 0; g < p.ngates; g++) {
+    for (int g = 0; g < (p.geo.debug == 2 ? 0 : p.ngates); g++) {
       const TileGateF& G = p.g[g];
       if (G.type == TG_Q2) {
 #ifndef QDC_F64
@@ -224,11 +321,11 @@ __global__ void __launch_bounds__(QDC_TILE_NT_F, 3)
           tile_apply<QDC_TILE_NT_F>(smv, geo, nvec / 2, G);
         }
       } else {
-        tile_diag<QDC_TILE_NT_F>(smv, nvec, G.re, G.im, G.a, G.b);
+        tile_diag<QDC_TILE_NT_F>(smv, nvec, G.m, G.a, G.b);
       }
       __syncthreads();
     }
-    tile_io<QDC_TILE_NT_F, false>((vec_t*)state, smv, ta, tbase);
+    if (p.geo.debug != 1) tile_io<QDC_TILE_NT_F, false>((vec_t*)state, smv, ta, tbase);
     __syncthreads();
   }
 }
@@ -241,7 +338,8 @@ __device__ __forceinline__ void tile_rev(vec_t* smf, vec_t* smb, const Geo& geo,
   // phase A: un-compute the state.  Phase B revisits the same items with the
   // same thread, so no barrier is needed in between; splitting keeps only one
   // gate matrix live at a time (register pressure).
-  for (int i = threadIdx.x; i < nitems; i += NT) {
+  for (int i0 = 0; i0 < nitems; i0 += NT) {  // uniform trip count (nitems % NT == 0): convergent loop
+    const int i = i0 + threadIdx.x;
     VecU vf[Geo::NVEC];
     const uint32_t base = geo.base32((uint32_t)i);
 #pragma unroll
@@ -249,13 +347,14 @@ __device__ __forceinline__ void tile_rev(vec_t* smf, vec_t* smb, const Geo& geo,
     cplx_t a[Geo::NG][K];
     Geo::unpack(vf, a);
 #pragma unroll
-    for (int e = 0; e < Geo::NG; e++) mv<K>(G.ire, G.iim, a[e]);
+    for (int e = 0; e < Geo::NG; e++) mv<K>(G.inv, a[e]);
     Geo::pack(vf, a);
 #pragma unroll
     for (int c = 0; c < Geo::NVEC; c++) smf[base + geo.off32(c)] = vf[c].v;
   }
   // phase B: gradient from (pre-gate state, post-gate adjoint), then pull the adjoint back
-  for (int i = threadIdx.x; i < nitems; i += NT) {
+  for (int i0 = 0; i0 < nitems; i0 += NT) {  // uniform trip count (nitems % NT == 0): convergent loop
+    const int i = i0 + threadIdx.x;
     VecU vf[Geo::NVEC], vb[Geo::NVEC];
     const uint32_t base = geo.base32((uint32_t)i);
 #pragma unroll
@@ -269,10 +368,10 @@ __device__ __forceinline__ void tile_rev(vec_t* smf, vec_t* smb, const Geo& geo,
       cplx_t a[Geo::NG][K];
       Geo::unpack(vf, a);
 #pragma unroll
-      for (int e = 0; e < Geo::NG; e++) outer_acc<K>(b[e], a[e], acc);
+      for (int e = 0; e < Geo::NG; e++) outer_tile<K>(b[e], a[e], acc);
     }
 #pragma unroll
-    for (int e = 0; e < Geo::NG; e++) mv<K>(G.tre, G.tim, b[e]);
+    for (int e = 0; e < Geo::NG; e++) mv<K>(G.tr, b[e]);
     Geo::pack(vb, b);
 #pragma unroll
     for (int c = 0; c < Geo::NVEC; c++) smb[base + geo.off32(c)] = vb[c].v;
@@ -281,7 +380,8 @@ __device__ __forceinline__ void tile_rev(vec_t* smf, vec_t* smb, const Geo& geo,
 
 template <int NT>
 __device__ __forceinline__ void tile_rev_diag(vec_t* smf, vec_t* smb, int nvec, const TileGateB& G, real_t* acc) {
-  for (int i = threadIdx.x; i < nvec; i += NT) {
+  for (int i0 = 0; i0 < nvec; i0 += NT) {  // uniform trip count
+    const int i = i0 + threadIdx.x;
     VecU vf, vb;
     vf.v = smf[i];
     vb.v = smb[i];
@@ -289,7 +389,7 @@ __device__ __forceinline__ void tile_rev_diag(vec_t* smf, vec_t* smb, int nvec, 
     for (int e = 0; e < QDC_VA; e++) {
       const int amp = i * QDC_VA + e;
       const int j = 2 * ((amp >> G.a) & 1) + ((amp >> G.b) & 1);
-      real_t dr = sel4(G.ire, j), di = sel4(G.iim, j);
+      real_t dr = gm_sel4_re(G.inv, j), di = gm_sel4_im(G.inv, j);
       const real_t fx = vf.r[2 * e] * dr - vf.r[2 * e + 1] * di, fy = vf.r[2 * e] * di + vf.r[2 * e + 1] * dr;
       vf.r[2 * e] = fx;
       vf.r[2 * e + 1] = fy;
@@ -302,8 +402,8 @@ __device__ __forceinline__ void tile_rev_diag(vec_t* smf, vec_t* smb, int nvec, 
           acc[2 * jj + 1] += (j == jj) ? pi : (real_t)0;
         }
       }
-      dr = sel4(G.tre, j);
-      di = sel4(G.tim, j);
+      dr = gm_sel4_re(G.tr, j);
+      di = gm_sel4_im(G.tr, j);
       vb.r[2 * e] = bx * dr - by * di;
       vb.r[2 * e + 1] = bx * di + by * dr;
     }
@@ -330,10 +430,12 @@ __global__ void __launch_bounds__(QDC_TILE_NT_B, 3)
   ta.init(p.geo);
   for (uint64_t tile = blockIdx.x; tile < p.geo.ntiles; tile += gridDim.x) {
     const uint64_t tbase = p.geo.tile(tile) >> QDC_LV;
-    tile_io<QDC_TILE_NT_B, true>((vec_t*)fwd, smf, ta, tbase);
-    tile_io<QDC_TILE_NT_B, true>((vec_t*)bwd, smb, ta, tbase);
+    if (p.geo.debug != 1) {
+      tile_io<QDC_TILE_NT_B, true>((vec_t*)fwd, smf, ta, tbase);
+      tile_io<QDC_TILE_NT_B, true>((vec_t*)bwd, smb, ta, tbase);
+    }
     __syncthreads();
-    for (int g = 0; g < p.ngates; g++) {
+    for (int g = 0; g < (p.geo.debug == 2 ? 0 : p.ngates); g++) {
       const TileGateB& G = p.g[g];
       real_t acc[32];
 #pragma unroll
@@ -381,8 +483,10 @@ __global__ void __launch_bounds__(QDC_TILE_NT_B, 3)
         sm_acc[g * 32 + lane] += s;
       }
     }
-    tile_io<QDC_TILE_NT_B, false>((vec_t*)fwd, smf, ta, tbase);
-    tile_io<QDC_TILE_NT_B, false>((vec_t*)bwd, smb, ta, tbase);
+    if (p.geo.debug != 1) {
+      tile_io<QDC_TILE_NT_B, false>((vec_t*)fwd, smf, ta, tbase);
+      tile_io<QDC_TILE_NT_B, false>((vec_t*)bwd, smb, ta, tbase);
+    }
     __syncthreads();
   }
   for (int i = threadIdx.x; i < p.ngates * 32; i += QDC_TILE_NT_B)
@@ -404,8 +508,10 @@ __global__ void k_tile_final(const double* __restrict__ partials, int ncta, int 
 }
 
 // ------------------------------------------------------------ host launch
+static int g_tile_debug = 0;
 static inline const char* make_tile_geo(const qdc::Plan& plan, const qdc::Step& t, int n_loc, int low_bits,
                                         TileGeo* geo, std::vector<int>* tile_pos_of) {
+  geo->debug = g_tile_debug;
   std::vector<int> bits(plan.tile_bits.begin() + t.tb_first, plan.tile_bits.begin() + t.tb_first + t.tb_count);
   // pad with the lowest unused positions so that T >= log2(threads * vector) and runs stay whole
   int T = (int)bits.size();
@@ -459,7 +565,8 @@ static inline const char* tile_grid(const void* kernel, int threads, size_t smem
 }
 
 // Fill the (hi,lo)-ordered matrix of a dense gate, or the 4 diagonal entries.
-static inline const char* tile_matrix(const cplx_t* gate, int kind, int form, bool swap, real_t* re, real_t* im) {
+static inline const char* tile_matrix(const cplx_t* gate, int kind, int form, bool swap, GateMat* out) {
+  real_t re[16], im[16];
   for (int i = 0; i < 16; i++) re[i] = im[i] = 0;
   if (kind_is_q1(kind)) {
     zc m[4];
@@ -476,6 +583,7 @@ static inline const char* tile_matrix(const cplx_t* gate, int kind, int form, bo
       im[j] = (form == FORM_CONJ_TR) ? -gate[j].y : gate[j].y;
     }
   }
+  gm_fill(*out, re, im);
   return nullptr;
 }
 
@@ -491,7 +599,7 @@ inline const char* Circuit::run_tile_forward(const qdc::Step& t, const std::vect
     TileGateF& G = p.g[k];
     G.pad = 0;
     const bool swap = st.p1 >= 0 && st.p2 < st.p1;
-    QDC_TRY(tile_matrix(gp[st.inst], kind, FORM_PLAIN, swap, G.re, G.im));
+    QDC_TRY(tile_matrix(gp[st.inst], kind, FORM_PLAIN, swap, &G.m));
     if (kind_is_q1(kind)) {
       G.type = TG_Q1;
       G.a = tpos[st.p2];
@@ -534,7 +642,7 @@ inline const char* Circuit::run_tile_backward(const qdc::Step& t, const std::vec
       TileGateF& G = p.g[k];
       G.pad = 0;
       const bool swap = st.p1 >= 0 && st.p2 < st.p1;
-      QDC_TRY(tile_matrix(gp[st.inst], kind, kind_is_nonu(kind) ? FORM_INV : FORM_CONJ_TR, swap, G.re, G.im));
+      QDC_TRY(tile_matrix(gp[st.inst], kind, kind_is_nonu(kind) ? FORM_INV : FORM_CONJ_TR, swap, &G.m));
       G.type = kind_is_q1(kind) ? TG_Q1 : (kind_is_q2dense(kind) ? TG_Q2 : TG_DIAG);
       if (G.type == TG_Q2) {
         G.a = tpos[swap ? st.p1 : st.p2];
@@ -568,8 +676,8 @@ inline const char* Circuit::run_tile_backward(const qdc::Step& t, const std::vec
     const int kind = insts_[st.inst].kind;
     TileGateB& G = p.g[k];
     const bool swap = st.p1 >= 0 && st.p2 < st.p1;
-    QDC_TRY(tile_matrix(gp[st.inst], kind, kind_is_nonu(kind) ? FORM_INV : FORM_CONJ_TR, swap, G.ire, G.iim));
-    QDC_TRY(tile_matrix(gp[st.inst], kind, kind_is_diag(kind) ? FORM_PLAIN : FORM_TR, swap, G.tre, G.tim));
+    QDC_TRY(tile_matrix(gp[st.inst], kind, kind_is_nonu(kind) ? FORM_INV : FORM_CONJ_TR, swap, &G.inv));
+    QDC_TRY(tile_matrix(gp[st.inst], kind, kind_is_diag(kind) ? FORM_PLAIN : FORM_TR, swap, &G.tr));
     G.type = kind_is_q1(kind) ? TG_Q1 : (kind_is_q2dense(kind) ? TG_Q2 : TG_DIAG);
     if (G.type == TG_Q2) {
       G.a = tpos[swap ? st.p1 : st.p2];

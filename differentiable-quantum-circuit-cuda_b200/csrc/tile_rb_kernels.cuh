@@ -13,6 +13,12 @@
 #pragma once
 #include "tile_kernels.cuh"
 
+#define QDC_TILE_NT_BRB 128  // threads per CTA of the register-blocked backward kernel
+#ifdef QDC_F64
+#define QDC_RB_FWD_MINB 4   // 16 double-complex amplitudes per thread: 128 registers
+#else
+#define QDC_RB_FWD_MINB 6
+#endif
 #define QDC_RB 4            // positions per register block
 #define QDC_RB_AMPS 16
 #define QDC_RB_MAXGRP 24
@@ -43,12 +49,12 @@ __host__ __device__ constexpr int rb_ins0(int i, int pos) { return ((i >> pos) <
 
 // ------------------------------------------------------------ forward ops
 template <int GA, int GB>
-__device__ __forceinline__ void rb_q2(cplx_t (&x)[QDC_RB_AMPS], const real_t (&re)[16], const real_t (&im)[16]) {
+__device__ __forceinline__ void rb_q2(cplx_t (&x)[QDC_RB_AMPS], const GateMat& G) {
 #pragma unroll
   for (int r = 0; r < 4; r++) {
     const int i0 = rb_ins0(rb_ins0(r, GB), GA);
     cplx_t a[4] = {x[i0], x[i0 + (1 << GB)], x[i0 + (1 << GA)], x[i0 + (1 << GA) + (1 << GB)]};
-    mv<4>(re, im, a);
+    mv<4>(G, a);
     x[i0] = a[0];
     x[i0 + (1 << GB)] = a[1];
     x[i0 + (1 << GA)] = a[2];
@@ -57,47 +63,46 @@ __device__ __forceinline__ void rb_q2(cplx_t (&x)[QDC_RB_AMPS], const real_t (&r
 }
 
 template <int P>
-__device__ __forceinline__ void rb_q1(cplx_t (&x)[QDC_RB_AMPS], const real_t (&re)[16], const real_t (&im)[16]) {
+__device__ __forceinline__ void rb_q1(cplx_t (&x)[QDC_RB_AMPS], const GateMat& G) {
 #pragma unroll
   for (int r = 0; r < 8; r++) {
     const int i0 = rb_ins0(r, P);
     cplx_t a[2] = {x[i0], x[i0 + (1 << P)]};
-    mv<2>(re, im, a);
+    mv<2>(G, a);
     x[i0] = a[0];
     x[i0 + (1 << P)] = a[1];
   }
 }
 
 template <int GA, int GB>
-__device__ __forceinline__ void rb_diag(cplx_t (&x)[QDC_RB_AMPS], const real_t (&re)[16], const real_t (&im)[16]) {
+__device__ __forceinline__ void rb_diag(cplx_t (&x)[QDC_RB_AMPS], const GateMat& G) {
 #pragma unroll
   for (int k = 0; k < QDC_RB_AMPS; k++) {
     const int j = 2 * ((k >> GA) & 1) + ((k >> GB) & 1);
-    const real_t xr = x[k].x * re[j] - x[k].y * im[j], xi = x[k].x * im[j] + x[k].y * re[j];
+    const real_t xr = x[k].x * gm_re(G, j) - x[k].y * gm_im(G, j), xi = x[k].x * gm_im(G, j) + x[k].y * gm_re(G, j);
     x[k].x = xr;
     x[k].y = xi;
   }
 }
 
-__device__ __forceinline__ void rb_apply(int code, cplx_t (&x)[QDC_RB_AMPS], const real_t (&re)[16],
-                                         const real_t (&im)[16]) {
+__device__ __forceinline__ void rb_apply(int code, cplx_t (&x)[QDC_RB_AMPS], const GateMat& G) {
   switch (code) {
-    case 0: rb_q2<1, 0>(x, re, im); break;
-    case 1: rb_q2<2, 0>(x, re, im); break;
-    case 2: rb_q2<2, 1>(x, re, im); break;
-    case 3: rb_q2<3, 0>(x, re, im); break;
-    case 4: rb_q2<3, 1>(x, re, im); break;
-    case 5: rb_q2<3, 2>(x, re, im); break;
-    case 6: rb_q1<0>(x, re, im); break;
-    case 7: rb_q1<1>(x, re, im); break;
-    case 8: rb_q1<2>(x, re, im); break;
-    case 9: rb_q1<3>(x, re, im); break;
-    case 10: rb_diag<1, 0>(x, re, im); break;
-    case 11: rb_diag<2, 0>(x, re, im); break;
-    case 12: rb_diag<2, 1>(x, re, im); break;
-    case 13: rb_diag<3, 0>(x, re, im); break;
-    case 14: rb_diag<3, 1>(x, re, im); break;
-    default: rb_diag<3, 2>(x, re, im); break;
+    case 0: rb_q2<1, 0>(x, G); break;
+    case 1: rb_q2<2, 0>(x, G); break;
+    case 2: rb_q2<2, 1>(x, G); break;
+    case 3: rb_q2<3, 0>(x, G); break;
+    case 4: rb_q2<3, 1>(x, G); break;
+    case 5: rb_q2<3, 2>(x, G); break;
+    case 6: rb_q1<0>(x, G); break;
+    case 7: rb_q1<1>(x, G); break;
+    case 8: rb_q1<2>(x, G); break;
+    case 9: rb_q1<3>(x, G); break;
+    case 10: rb_diag<1, 0>(x, G); break;
+    case 11: rb_diag<2, 0>(x, G); break;
+    case 12: rb_diag<2, 1>(x, G); break;
+    case 13: rb_diag<3, 0>(x, G); break;
+    case 14: rb_diag<3, 1>(x, G); break;
+    default: rb_diag<3, 2>(x, G); break;
   }
 }
 
@@ -112,7 +117,7 @@ __device__ __forceinline__ void rb_offsets(const RbGroup& G, uint32_t (&off)[QDC
   }
 }
 
-__global__ void __launch_bounds__(QDC_TILE_NT_F, 2)
+__global__ void __launch_bounds__(QDC_TILE_NT_F, QDC_RB_FWD_MINB)
     k_tile_fwd_rb(cplx_t* __restrict__ state, const __grid_constant__ TileFwdRbParams p) {
   extern __shared__ __align__(16) unsigned char tile_smem[];
   vec_t* smv = (vec_t*)tile_smem;
@@ -128,14 +133,15 @@ __global__ void __launch_bounds__(QDC_TILE_NT_F, 2)
       const RbGroup& G = p.grp[gi];
       uint32_t off[QDC_RB_AMPS];
       rb_offsets(G, off);
-      for (int j = threadIdx.x; j < nblocks; j += QDC_TILE_NT_F) {
+      for (int j0 = 0; j0 < nblocks; j0 += QDC_TILE_NT_F) {  // uniform trip count: nblocks % CTA size == 0
+        const int j = j0 + threadIdx.x;
         const uint32_t base = (uint32_t)G.map((uint64_t)j);
         cplx_t x[QDC_RB_AMPS];
 #pragma unroll
         for (int k = 0; k < QDC_RB_AMPS; k++) x[k] = sme[base + off[k]];
         for (int q = 0; q < G.count; q++) {
           const TileGateF& M = p.g[G.first + q];
-          rb_apply(M.type, x, M.re, M.im);
+          rb_apply(M.type, x, M.m);
         }
 #pragma unroll
         for (int k = 0; k < QDC_RB_AMPS; k++) sme[base + off[k]] = x[k];
@@ -156,7 +162,7 @@ __device__ __forceinline__ void rb_q2_rev(cplx_t (&xf)[QDC_RB_AMPS], cplx_t (&xb
   for (int r = 0; r < 4; r++) {
     const int i0 = rb_ins0(rb_ins0(r, GB), GA);
     cplx_t a[4] = {xf[i0], xf[i0 + (1 << GB)], xf[i0 + (1 << GA)], xf[i0 + (1 << GA) + (1 << GB)]};
-    mv<4>(M.ire, M.iim, a);
+    mv<4>(M.inv, a);
     xf[i0] = a[0];
     xf[i0 + (1 << GB)] = a[1];
     xf[i0 + (1 << GA)] = a[2];
@@ -168,9 +174,9 @@ __device__ __forceinline__ void rb_q2_rev(cplx_t (&xf)[QDC_RB_AMPS], cplx_t (&xb
     cplx_t b[4] = {xb[i0], xb[i0 + (1 << GB)], xb[i0 + (1 << GA)], xb[i0 + (1 << GA) + (1 << GB)]};
     if (M.slot >= 0) {
       const cplx_t a[4] = {xf[i0], xf[i0 + (1 << GB)], xf[i0 + (1 << GA)], xf[i0 + (1 << GA) + (1 << GB)]};
-      outer_acc<4>(b, a, acc);
+      outer_tile<4>(b, a, acc);
     }
-    mv<4>(M.tre, M.tim, b);
+    mv<4>(M.tr, b);
     xb[i0] = b[0];
     xb[i0 + (1 << GB)] = b[1];
     xb[i0 + (1 << GA)] = b[2];
@@ -185,12 +191,12 @@ __device__ __forceinline__ void rb_q1_rev(cplx_t (&xf)[QDC_RB_AMPS], cplx_t (&xb
   for (int r = 0; r < 8; r++) {
     const int i0 = rb_ins0(r, P);
     cplx_t a[2] = {xf[i0], xf[i0 + (1 << P)]};
-    mv<2>(M.ire, M.iim, a);
+    mv<2>(M.inv, a);
     xf[i0] = a[0];
     xf[i0 + (1 << P)] = a[1];
     cplx_t b[2] = {xb[i0], xb[i0 + (1 << P)]};
-    if (M.slot >= 0) outer_acc<2>(b, a, acc);
-    mv<2>(M.tre, M.tim, b);
+    if (M.slot >= 0) outer_tile<2>(b, a, acc);
+    mv<2>(M.tr, b);
     xb[i0] = b[0];
     xb[i0 + (1 << P)] = b[1];
   }
@@ -202,7 +208,7 @@ __device__ __forceinline__ void rb_diag_rev(cplx_t (&xf)[QDC_RB_AMPS], cplx_t (&
 #pragma unroll
   for (int k = 0; k < QDC_RB_AMPS; k++) {
     const int j = 2 * ((k >> GA) & 1) + ((k >> GB) & 1);
-    const real_t fx = xf[k].x * M.ire[j] - xf[k].y * M.iim[j], fy = xf[k].x * M.iim[j] + xf[k].y * M.ire[j];
+    const real_t fx = xf[k].x * gm_re(M.inv, j) - xf[k].y * gm_im(M.inv, j), fy = xf[k].x * gm_im(M.inv, j) + xf[k].y * gm_re(M.inv, j);
     xf[k].x = fx;
     xf[k].y = fy;
     const real_t bx = xb[k].x, by = xb[k].y;
@@ -210,8 +216,8 @@ __device__ __forceinline__ void rb_diag_rev(cplx_t (&xf)[QDC_RB_AMPS], cplx_t (&
       acc[2 * j] += bx * fx - by * fy;
       acc[2 * j + 1] += bx * fy + by * fx;
     }
-    xb[k].x = bx * M.tre[j] - by * M.tim[j];
-    xb[k].y = bx * M.tim[j] + by * M.tre[j];
+    xb[k].x = bx * gm_re(M.tr, j) - by * gm_im(M.tr, j);
+    xb[k].y = bx * gm_im(M.tr, j) + by * gm_re(M.tr, j);
   }
 }
 
@@ -241,7 +247,7 @@ __device__ __forceinline__ void rb_apply_rev(int code, cplx_t (&xf)[QDC_RB_AMPS]
 // Gradient partials: thread -> warp reduce-scatter (lane j owns value j) -> the
 // warp's private row of `part` (no atomics, fixed order) -> at the end of every
 // tile warp-ordered sum into the CTA's double accumulators.
-__global__ void __launch_bounds__(QDC_TILE_NT_B, 3)
+__global__ void __launch_bounds__(QDC_TILE_NT_BRB, 3)
     k_tile_bwd_rb(cplx_t* __restrict__ fwd, cplx_t* __restrict__ bwd, const __grid_constant__ TileBwdRbParams p,
                   double* __restrict__ partials) {
   extern __shared__ __align__(16) unsigned char tile_smem[];
@@ -252,25 +258,26 @@ __global__ void __launch_bounds__(QDC_TILE_NT_B, 3)
   cplx_t* eb = (cplx_t*)smb;
   double* sm_acc = (double*)(smb + nvec);
   real_t* part = (real_t*)(sm_acc + QDC_TILE_MAXG_B * 32);
-  constexpr int NW = QDC_TILE_NT_B / 32;
+  constexpr int NW = QDC_TILE_NT_BRB / 32;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nblocks = 1 << (p.geo.T - QDC_RB);
-  for (int i = threadIdx.x; i < QDC_TILE_MAXG_B * 32; i += QDC_TILE_NT_B) sm_acc[i] = 0.0;
-  for (int i = threadIdx.x; i < NW * QDC_TILE_MAXG_B * 32; i += QDC_TILE_NT_B) part[i] = 0;
+  for (int i = threadIdx.x; i < QDC_TILE_MAXG_B * 32; i += QDC_TILE_NT_BRB) sm_acc[i] = 0.0;
+  for (int i = threadIdx.x; i < NW * QDC_TILE_MAXG_B * 32; i += QDC_TILE_NT_BRB) part[i] = 0;
   __syncthreads();
-  TileAddr<QDC_TILE_NT_B> ta;
+  TileAddr<QDC_TILE_NT_BRB> ta;
   ta.init(p.geo);
   real_t* mypart = part + (size_t)warp * QDC_TILE_MAXG_B * 32;
   for (uint64_t tile = blockIdx.x; tile < p.geo.ntiles; tile += gridDim.x) {
     const uint64_t tbase = p.geo.tile(tile) >> QDC_LV;
-    tile_io<QDC_TILE_NT_B, true>((vec_t*)fwd, smf, ta, tbase);
-    tile_io<QDC_TILE_NT_B, true>((vec_t*)bwd, smb, ta, tbase);
+    tile_io<QDC_TILE_NT_BRB, true>((vec_t*)fwd, smf, ta, tbase);
+    tile_io<QDC_TILE_NT_BRB, true>((vec_t*)bwd, smb, ta, tbase);
     __syncthreads();
     for (int gi = 0; gi < p.ngroups; gi++) {
       const RbGroup& G = p.grp[gi];
       uint32_t off[QDC_RB_AMPS];
       rb_offsets(G, off);
-      for (int j = threadIdx.x; j < nblocks; j += QDC_TILE_NT_B) {  // nblocks is a multiple of the CTA size
+      for (int j0 = 0; j0 < nblocks; j0 += QDC_TILE_NT_BRB) {  // uniform trip count: nblocks % CTA size == 0
+        const int j = j0 + threadIdx.x;
         const uint32_t base = (uint32_t)G.map((uint64_t)j);
         cplx_t xf[QDC_RB_AMPS], xb[QDC_RB_AMPS];
 #pragma unroll
@@ -300,7 +307,7 @@ __global__ void __launch_bounds__(QDC_TILE_NT_B, 3)
       __syncthreads();
     }
     // fold this tile's per-warp partials into the CTA accumulators (fixed order)
-    for (int i = threadIdx.x; i < p.ngates * 32; i += QDC_TILE_NT_B) {
+    for (int i = threadIdx.x; i < p.ngates * 32; i += QDC_TILE_NT_BRB) {
       double s = 0.0;
 #pragma unroll
       for (int w = 0; w < NW; w++) {
@@ -309,11 +316,11 @@ __global__ void __launch_bounds__(QDC_TILE_NT_B, 3)
       }
       sm_acc[i] += s;
     }
-    tile_io<QDC_TILE_NT_B, false>((vec_t*)fwd, smf, ta, tbase);
-    tile_io<QDC_TILE_NT_B, false>((vec_t*)bwd, smb, ta, tbase);
+    tile_io<QDC_TILE_NT_BRB, false>((vec_t*)fwd, smf, ta, tbase);
+    tile_io<QDC_TILE_NT_BRB, false>((vec_t*)bwd, smb, ta, tbase);
     __syncthreads();
   }
-  for (int i = threadIdx.x; i < p.ngates * 32; i += QDC_TILE_NT_B)
+  for (int i = threadIdx.x; i < p.ngates * 32; i += QDC_TILE_NT_BRB)
     partials[(size_t)blockIdx.x * p.ngates * 32 + i] = sm_acc[i];
 }
 
@@ -373,13 +380,15 @@ static inline const char* rb_make_groups(const qdc::Plan& plan, const qdc::Step&
 }
 
 // diagonal entries in (hi,lo) order
-static inline void rb_diag_entries(const cplx_t* d, bool swap, bool conj, real_t* re, real_t* im) {
+static inline void rb_diag_entries(const cplx_t* d, bool swap, bool conj, GateMat* out) {
+  real_t re[16], im[16];
   for (int i = 0; i < 16; i++) re[i] = im[i] = 0;
   for (int j = 0; j < 4; j++) {
     const int src = swap ? perm2(j) : j;
     re[j] = d[src].x;
     im[j] = conj ? -d[src].y : d[src].y;
   }
+  gm_fill(*out, re, im);
 }
 
 // Build the gate table of a pass for the register-blocked kernels.
@@ -425,9 +434,9 @@ inline const char* Circuit::run_tile_forward_rb(const qdc::Step& t, const std::v
     G.a = G.b = G.pad = 0;
     const int form = uncompute ? (kind_is_nonu(kind) ? FORM_INV : FORM_CONJ_TR) : FORM_PLAIN;
     if (kind_is_diag(kind)) {
-      rb_diag_entries(gp[st.inst], swap_of[src], uncompute, G.re, G.im);
+      rb_diag_entries(gp[st.inst], swap_of[src], uncompute, &G.m);
     } else {
-      QDC_TRY(tile_matrix(gp[st.inst], kind, form, swap_of[src], G.re, G.im));
+      QDC_TRY(tile_matrix(gp[st.inst], kind, form, swap_of[src], &G.m));
     }
   }
   const size_t smem = sizeof(cplx_t) << p.geo.T;
@@ -461,22 +470,21 @@ inline const char* Circuit::run_tile_backward_rb(const qdc::Step& t, const std::
     G.type = code_of[src];
     G.a = G.b = 0;
     if (kind_is_diag(kind)) {
-      rb_diag_entries(gp[st.inst], swap_of[src], true, G.ire, G.iim);
-      rb_diag_entries(gp[st.inst], swap_of[src], false, G.tre, G.tim);
+      rb_diag_entries(gp[st.inst], swap_of[src], true, &G.inv);
+      rb_diag_entries(gp[st.inst], swap_of[src], false, &G.tr);
       diag_hilo_[st.inst] = swap_of[src];
     } else {
-      QDC_TRY(tile_matrix(gp[st.inst], kind, kind_is_nonu(kind) ? FORM_INV : FORM_CONJ_TR, swap_of[src], G.ire,
-                          G.iim));
-      QDC_TRY(tile_matrix(gp[st.inst], kind, FORM_TR, swap_of[src], G.tre, G.tim));
+      QDC_TRY(tile_matrix(gp[st.inst], kind, kind_is_nonu(kind) ? FORM_INV : FORM_CONJ_TR, swap_of[src], &G.inv));
+      QDC_TRY(tile_matrix(gp[st.inst], kind, FORM_TR, swap_of[src], &G.tr));
     }
     G.slot = (int)vslot[st.inst];
     h_slots.s[k] = G.slot;
   }
   const size_t tile_bytes = sizeof(cplx_t) << p.geo.T;
   const size_t smem = 2 * tile_bytes + QDC_TILE_MAXG_B * 32 * sizeof(double) +
-                      (QDC_TILE_NT_B / 32) * QDC_TILE_MAXG_B * 32 * sizeof(real_t);
+                      (QDC_TILE_NT_BRB / 32) * QDC_TILE_MAXG_B * 32 * sizeof(real_t);
   int grid = 0;
-  QDC_TRY(tile_grid((const void*)k_tile_bwd_rb, QDC_TILE_NT_B, smem, p.geo.ntiles, &grid));
+  QDC_TRY(tile_grid((const void*)k_tile_bwd_rb, QDC_TILE_NT_BRB, smem, p.geo.ntiles, &grid));
   const size_t need = (size_t)grid * QDC_TILE_MAXG_B * 32;
   if (need > tile_partials_cap_) {
     if (tile_partials_) QDC_CUDA(cudaFree(tile_partials_));
@@ -485,7 +493,7 @@ inline const char* Circuit::run_tile_backward_rb(const qdc::Step& t, const std::
   }
   cudaEvent_t pa = nullptr;
   if (prof_.on) pa = prof_.begin(stream_);
-  k_tile_bwd_rb<<<grid, QDC_TILE_NT_B, smem, stream_>>>(state_, bwd_, p, tile_partials_);
+  k_tile_bwd_rb<<<grid, QDC_TILE_NT_BRB, smem, stream_>>>(state_, bwd_, p, tile_partials_);
   QDC_CUDA(cudaGetLastError());
   k_tile_final<<<t.count, 32, 0, stream_>>>(tile_partials_, grid, t.count, h_slots, d_res_);
   QDC_CUDA(cudaGetLastError());
