@@ -81,6 +81,49 @@ def brickwork_inputs(n, depth, dtype):
     return var, cts
 
 
+def vqse_program(n, layers):
+    """example_vqse_ising.py:66-79: per layer n ring ZZ diagonal gates + n X rotations; n ring densities."""
+    prog = []
+    for _ in range(layers):
+        for i in range(n - 1):
+            prog.append(("diag", i, i + 1))
+        prog.append(("diag", 0, n - 1))
+        for i in range(n):
+            prog.append(("q1", i, -1))
+    dens = [(i, i + 1) for i in range(n - 1)] + [(0, n - 1)]
+    return prog, dens
+
+
+def build_vqse(circuit, n, layers):
+    prog, dens = vqse_program(n, layers)
+    for kind, a, b in prog:
+        if kind == "diag":
+            circuit.add_q2_var_gate_diag(a, b)
+        else:
+            circuit.add_q1_var_gate(a)
+    for a, b in dens:
+        circuit.get_q2_dens_op_with_grad(a, b)
+    return len(prog), len(dens)
+
+
+def vqse_inputs(n, layers, dtype):
+    """Gates of example_vqse_ising.py:15-28 from 2*layers N(0,1) parameters (seed 42); cotangent = h^T of the
+    transverse-field Ising two-site term (:86-93)."""
+    rng = np.random.default_rng(42)
+    params = rng.normal(size=2 * layers)
+    var = []
+    for l in range(layers):
+        g, b = params[2 * l], params[2 * l + 1]
+        zz = np.array([np.exp(-1j * g), np.exp(1j * g), np.exp(1j * g), np.exp(-1j * g)], dtype=dtype)
+        x = np.array([np.cos(b), -1j * np.sin(b), -1j * np.sin(b), np.cos(b)], dtype=dtype)
+        var += n * [zz] + n * [x]
+    sz = np.diag([1.0, -1.0]); sx = np.array([[0, 1.0], [1.0, 0]]); eye = np.eye(2)
+    k = lambda a, b: np.tensordot(a, b, axes=0).transpose(0, 2, 1, 3).reshape(4, 4)  # noqa: E731
+    h = (-k(sz, sz) - 0.5 * (k(sx, eye) + k(eye, sx))).astype(dtype)
+    _, dens = vqse_program(n, layers)
+    return var, [h.T.copy() for _ in dens]
+
+
 # -------------------------------------------------------------------- clocks
 class ClockSampler:
     """Samples nvidia-smi clocks / throttle reasons during the timed region."""
@@ -194,8 +237,14 @@ def run_ours(args):
         circ.set_option("max_tile_gates", args.max_tile_gates)
     if args.tile_debug:
         circ.set_option("tile_debug", args.tile_debug)
-    n_gates, n_dens = build_brickwork(circ, n_total, args.depth)
-    var, cts = brickwork_inputs(n_total, args.depth, dtype)
+    if args.workload == "vqse":
+        n_gates, n_dens = build_vqse(circ, n_total, args.depth)
+        var, cts = vqse_inputs(n_total, args.depth, dtype)
+        if world == 1:
+            circ.set_state_from_vector((np.ones(1 << n_total) / np.sqrt(float(1 << n_total))).astype(dtype))
+    else:
+        n_gates, n_dens = build_brickwork(circ, n_total, args.depth)
+        var, cts = brickwork_inputs(n_total, args.depth, dtype)
     cts_conj = [c.conj() for c in cts]
     h2d = sum(v.nbytes for v in var) * 2 + sum(c.nbytes for c in cts)   # gates go in twice (fwd, bwd)
     d2h = n_dens * 16 * var[0].itemsize + sum(v.nbytes for v in var)
@@ -277,7 +326,7 @@ def run_ours(args):
         "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(dev_ms / args.steps, 3), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-        "config": {"workload": f"brickwork-{n_total}q-depth{args.depth}-{args.precision}", "qubits": n_total,
+        "config": {"workload": f"{args.workload}-{n_total}q-depth{args.depth}-{args.precision}", "qubits": n_total,
                    "local_qubits": args.qubits, "depth": args.depth, "gates": n_gates, "densities": n_dens,
                    "state_bytes_per_gpu": int(np.dtype(dtype).itemsize) << args.qubits,
                    "unit_note": "one gate-apply = one gate applied (fwd+bwd) to one 2^local_qubits-amplitude shard; "
@@ -362,7 +411,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--qubits", type=int, default=32, help="LOCAL qubits per GPU (total = qubits + log2(gpus))")
-    ap.add_argument("--depth", type=int, default=100)
+    ap.add_argument("--depth", type=int, default=100, help="brickwork layers / VQSE (ZZ, X) layer pairs")
+    ap.add_argument("--workload", default="brickwork", choices=["brickwork", "vqse"])
     ap.add_argument("--ref-depth", type=int, default=2, help="depth of the bounded sample the reference arm runs")
     ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
     ap.add_argument("--fuse", type=int, default=2, help="0: one pass per gate, 1: tiled passes, 2: register-blocked tiled passes")
