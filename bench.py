@@ -237,6 +237,8 @@ def run_ours(args):
         circ.set_option("max_tile_gates", args.max_tile_gates)
     if args.tile_debug:
         circ.set_option("tile_debug", args.tile_debug)
+    if world > 1:
+        circ.set_option("peer", args.peer)
     if args.workload == "vqse":
         n_gates, n_dens = build_vqse(circ, n_total, args.depth)
         var, cts = vqse_inputs(n_total, args.depth, dtype)
@@ -333,6 +335,8 @@ def run_ours(args):
                                 "an N-GPU run applies each gate to N shards",
                    "full_state_gate_applies_per_s": round(n_gates * args.steps / (dev_ms * 1e-3), 3),
                    "l2": "inputs (state + adjoint) far larger than L2; no flush needed",
+                   "exchange": (("peer-memory swap kernel (NVLink, CUDA IPC)" if circ.peer_exchange else
+                                 "NCCL send/recv + pack/unpack") if world > 1 else None),
                    "executor": ["one pass per gate", "tiled multi-gate passes", "register-blocked tiled passes"][args.fuse]},
         "effective_hbm_gbs": round(total_alg * world / (dev_ms * 1e-3) / 1e9, 1),
         "effective_hbm_frac": round(total_alg / (dev_ms * 1e-3) / 1e9 / peak, 4),
@@ -419,6 +423,7 @@ def main():
     ap.add_argument("--tile-bits", type=int, default=0, help="T of the tiled passes (0: library default)")
     ap.add_argument("--low-bits", type=int, default=0, help="L lowest positions forced into every tile (0: default)")
     ap.add_argument("--max-tile-gates", type=int, default=0)
+    ap.add_argument("--peer", type=int, default=1, help="sharded: 1 peer-memory swap kernel, 0 NCCL send/recv")
     ap.add_argument("--tile-debug", type=int, default=0, help="profiling aid (1: no HBM traffic, 2: no gates); invalid results")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -50,6 +50,7 @@ _CIRCUIT_SIGNATURES = {
     "qdc_circuit_new": (_err, [C.POINTER(C.c_void_p), _sz]),
     "qdc_circuit_new_sharded": (_err, [C.POINTER(C.c_void_p), _sz, C.c_int, C.c_int, C.c_void_p]),
     "qdc_nccl_unique_id": (_err, [C.c_void_p]),
+    "qdc_circuit_peer_exchange": (C.c_int, [C.c_void_p]),
     "qdc_circuit_free": (_err, [C.c_void_p]),
     "qdc_circuit_set_state_from_host": (_err, [C.c_void_p, c_cplx_p, _sz]),
     "qdc_circuit_add": (_err, [C.c_void_p, C.c_int, _sz, _sz]),

@@ -139,6 +139,45 @@ __global__ void __launch_bounds__(QDC_BLOCK)
   }
 }
 
+// ---- qubit-remap swap fused with the exchange, over NVLink peer memory -----
+// new[lpos = b, rank bit = c] = old[lpos = c, rank bit = b]: the element
+// (lpos = 1-c, x) of this rank trades places with the element (lpos = c, x) of
+// the partner.  Every such PAIR is owned by exactly one of the two GPUs (the
+// x range is split in halves by rank bit), which loads both elements -- the
+// partner's through its peer mapping -- and stores them swapped.  No staging
+// buffer, no pack / unpack passes, in place on both GPUs, and no thread ever
+// waits on the other GPU (ordering is by stream-ordered token exchanges
+// before and after the kernel).
+template <typename V>
+__global__ void __launch_bounds__(QDC_BLOCK)
+    k_peer_swap(V* __restrict__ mine, V* __restrict__ peer, int pos, int c, uint64_t x_begin, uint64_t x_end) {
+  const uint64_t stride = (uint64_t)gridDim.x * QDC_BLOCK;
+  constexpr int U = 4;
+  for (uint64_t x0 = x_begin + (uint64_t)blockIdx.x * QDC_BLOCK + threadIdx.x; x0 < x_end; x0 += stride * U) {
+    V a[U], b[U];
+    uint64_t mi[U], pi[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const uint64_t x = x0 + (uint64_t)u * stride;
+      const uint64_t base = ins0(x, pos);
+      mi[u] = base | ((uint64_t)(1 - c) << pos);
+      pi[u] = base | ((uint64_t)c << pos);
+      if (x < x_end) {
+        a[u] = mine[mi[u]];
+        b[u] = peer[pi[u]];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const uint64_t x = x0 + (uint64_t)u * stride;
+      if (x < x_end) {
+        mine[mi[u]] = b[u];
+        peer[pi[u]] = a[u];
+      }
+    }
+  }
+}
+
 class Circuit {
  public:
   explicit Circuit(int n) : n_(n), n_loc_(n) {}
@@ -152,8 +191,15 @@ class Circuit {
   cplx_t* state_ = nullptr;
   cplx_t* bwd_ = nullptr;
   cplx_t* initial_ = nullptr;  // nullptr <=> |0..0>
-  cplx_t* stage_a_ = nullptr;  // exchange staging (half shard each)
+  cplx_t* stage_a_ = nullptr;  // exchange staging (half shard each; NCCL path only)
   cplx_t* stage_b_ = nullptr;
+  // peer-memory exchange: partner buffers mapped with CUDA IPC
+  static constexpr int kMaxWorld = 64;
+  cplx_t* peer_state_[kMaxWorld] = {nullptr};
+  cplx_t* peer_bwd_[kMaxWorld] = {nullptr};
+  bool peer_ok_ = false;
+  int opt_peer_ = 1;          // 1: peer-memory swap kernel when available, 0: NCCL send/recv + pack/unpack
+  int* d_token_ = nullptr;    // 2 ints: tokens of the stream-ordered pairwise barriers
   Workspace ws_;
   double* d_res_ = nullptr;  // device results: 32 doubles per slot
   size_t d_res_slots_ = 0;
@@ -181,6 +227,13 @@ class Circuit {
     d_res_slots_ = 0;
     ws_release(ws_);
     release_tiles();
+    for (int r = 0; r < kMaxWorld; r++) {
+      if (peer_state_[r]) cudaIpcCloseMemHandle(peer_state_[r]);
+      if (peer_bwd_[r]) cudaIpcCloseMemHandle(peer_bwd_[r]);
+      peer_state_[r] = peer_bwd_[r] = nullptr;
+    }
+    if (d_token_) cudaFree(d_token_);
+    d_token_ = nullptr;
     if (comm_) {
       qdc::nccl().CommDestroy(comm_);
       comm_ = nullptr;
@@ -215,7 +268,62 @@ class Circuit {
       const int rc = qdc::nccl().CommInitRank(&comm_, world, id, rank);
       if (rc != 0) return qdc_errf("ncclCommInitRank failed: %s", qdc::nccl().GetErrorString(rc));
     }
-    return ensure_state();
+    QDC_TRY(ensure_state());
+    if (world > 1) {
+      QDC_CUDA(cudaMalloc((void**)&bwd_, bytes()));  // mapped by the partners: allocate up front
+      QDC_CUDA(cudaMalloc((void**)&d_token_, 2 * sizeof(int)));
+      QDC_CUDA(cudaMemset(d_token_, 0, 2 * sizeof(int)));
+      setup_peers();
+    }
+    return nullptr;
+  }
+
+  // Map the partners' state / adjoint buffers (CUDA IPC).  Any failure just
+  // leaves the NCCL send/recv path in charge.
+  void setup_peers() {
+    peer_ok_ = false;
+    if (world_ > kMaxWorld) return;
+    struct Handles { cudaIpcMemHandle_t s, b; };
+    Handles mine;
+    if (cudaIpcGetMemHandle(&mine.s, state_) != cudaSuccess || cudaIpcGetMemHandle(&mine.b, bwd_) != cudaSuccess) {
+      cudaGetLastError();
+      return;
+    }
+    Handles *d_mine = nullptr, *d_all = nullptr;
+    std::vector<Handles> all(world_);
+    bool ok = cudaMalloc((void**)&d_mine, sizeof(Handles)) == cudaSuccess &&
+              cudaMalloc((void**)&d_all, sizeof(Handles) * world_) == cudaSuccess;
+    if (ok) ok = cudaMemcpy(d_mine, &mine, sizeof(Handles), cudaMemcpyHostToDevice) == cudaSuccess;
+    if (ok) ok = qdc::nccl().AllGather(d_mine, d_all, sizeof(Handles), qdc::kNcclChar, comm_, stream_) == 0;
+    if (ok) ok = cudaStreamSynchronize(stream_) == cudaSuccess;
+    if (ok) ok = cudaMemcpy(all.data(), d_all, sizeof(Handles) * world_, cudaMemcpyDeviceToHost) == cudaSuccess;
+    if (d_mine) cudaFree(d_mine);
+    if (d_all) cudaFree(d_all);
+    int mapped = ok ? 1 : 0;
+    for (int j = 0; ok && (1 << j) < world_; j++) {
+      const int p = rank_ ^ (1 << j);
+      void *ps = nullptr, *pb = nullptr;
+      if (cudaIpcOpenMemHandle(&ps, all[p].s, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+          cudaIpcOpenMemHandle(&pb, all[p].b, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        mapped = 0;
+        break;
+      }
+      peer_state_[p] = (cplx_t*)ps;
+      peer_bwd_[p] = (cplx_t*)pb;
+    }
+    // every rank must take the same path: agree on success with an all-reduce (min via sum of failures)
+    int* d_flag = nullptr;
+    int fails = mapped ? 0 : 1, total = 1;
+    if (cudaMalloc((void**)&d_flag, sizeof(int)) == cudaSuccess) {
+      cudaMemcpy(d_flag, &fails, sizeof(int), cudaMemcpyHostToDevice);
+      // int32 sum: ncclInt32 = 2
+      if (qdc::nccl().AllReduce(d_flag, d_flag, 1, 2, qdc::kNcclSum, comm_, stream_) == 0 &&
+          cudaStreamSynchronize(stream_) == cudaSuccess)
+        cudaMemcpy(&total, d_flag, sizeof(int), cudaMemcpyDeviceToHost);
+      cudaFree(d_flag);
+    }
+    peer_ok_ = (total == 0);
   }
 
   const char* ensure_results(size_t slots) {
@@ -458,7 +566,44 @@ class Circuit {
   // new[lpos=b, rank bit=c] = old[lpos=c, rank bit=b].  This rank keeps its
   // half lpos == c and trades its half lpos == 1-c for the partner's half
   // lpos == c (the partner sees the mirror image).
+  // Stream-ordered rendezvous with one partner: returns (on the stream) only
+  // after the partner's stream has reached the matching call.
+  const char* pair_barrier(int partner) {
+    qdc::NcclApi& api = qdc::nccl();
+    int rc = api.GroupStart();
+    if (rc == 0) rc = api.Send(d_token_, sizeof(int), qdc::kNcclChar, partner, comm_, stream_);
+    if (rc == 0) rc = api.Recv(d_token_ + 1, sizeof(int), qdc::kNcclChar, partner, comm_, stream_);
+    const int rc2 = api.GroupEnd();
+    if (rc == 0) rc = rc2;
+    if (rc != 0) return qdc_errf("NCCL barrier failed: %s", api.GetErrorString(rc));
+    return nullptr;
+  }
+
+  const char* exchange_peer(cplx_t* buf, int gbit, int lpos) {
+    const int c = (rank_ >> gbit) & 1, partner = rank_ ^ (1 << gbit);
+    cplx_t* peer = (buf == state_) ? peer_state_[partner] : peer_bwd_[partner];
+    DeviceInfo di;
+    QDC_TRY(qdc_device_info(&di));
+    QDC_TRY(pair_barrier(partner));  // both GPUs are done with everything before the swap
+    if (lpos >= QDC_LV) {
+      const uint64_t nhalf = 1ull << (n_loc_ - 1 - QDC_LV);
+      const uint64_t lo = c ? nhalf / 2 : 0, hi = c ? nhalf : nhalf / 2;
+      const int grid = pick_grid(hi - lo, 4, 8, di.sm_count);
+      k_peer_swap<vec_t><<<grid, QDC_BLOCK, 0, stream_>>>((vec_t*)buf, (vec_t*)peer, lpos - QDC_LV, c, lo, hi);
+    } else {
+      const uint64_t nhalf = 1ull << (n_loc_ - 1);
+      const uint64_t lo = c ? nhalf / 2 : 0, hi = c ? nhalf : nhalf / 2;
+      const int grid = pick_grid(hi - lo, 4, 8, di.sm_count);
+      k_peer_swap<cplx_t><<<grid, QDC_BLOCK, 0, stream_>>>(buf, peer, lpos, c, lo, hi);
+    }
+    QDC_CUDA(cudaGetLastError());
+    QDC_TRY(pair_barrier(partner));  // the partner's half of the pairs has landed here too
+    account(1, 1, 0);
+    return nullptr;
+  }
+
   const char* exchange(cplx_t* buf, int gbit, int lpos) {
+    if (peer_ok_ && opt_peer_) return exchange_peer(buf, gbit, lpos);
     QDC_TRY(ensure_staging());
     const int c = (rank_ >> gbit) & 1, partner = rank_ ^ (1 << gbit);
     const size_t half_bytes = bytes() / 2;
@@ -613,7 +758,7 @@ class Circuit {
     const size_t nvar = count(2);
     QDC_TRY(ensure_results(nvar));
     if (nvar) QDC_CUDA(cudaMemsetAsync(d_res_, 0, nvar * 32 * sizeof(double), stream_));
-    if (!bwd_) QDC_CUDA(cudaMalloc((void**)&bwd_, bytes()));
+    if (!bwd_) QDC_CUDA(cudaMalloc((void**)&bwd_, bytes()));  // (sharded mode allocated it in shard())
 
     // variable-gate slot of every instruction
     std::vector<long> vslot(insts_.size(), -1);

@@ -27,6 +27,7 @@ struct NcclApi {
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
 
   const char* load() {
@@ -48,6 +49,7 @@ struct NcclApi {
     QDC_SYM(GroupStart, "ncclGroupStart")
     QDC_SYM(GroupEnd, "ncclGroupEnd")
     QDC_SYM(AllReduce, "ncclAllReduce")
+    QDC_SYM(AllGather, "ncclAllGather")
     QDC_SYM(GetErrorString, "ncclGetErrorString")
 #undef QDC_SYM
     return nullptr;

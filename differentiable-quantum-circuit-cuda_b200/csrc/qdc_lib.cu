@@ -107,6 +107,10 @@ QDC_EXPORT const char* qdc_circuit_state_device_ptr(qdc_circuit* c, void** devic
   return nullptr;
 }
 
+// 1 when exchanges run as the peer-memory swap kernel (CUDA IPC mapping of the
+// partners' buffers succeeded on every rank), 0 when they use NCCL send/recv.
+QDC_EXPORT int qdc_circuit_peer_exchange(const qdc_circuit* c) { return c->impl.peer_ok_ && c->impl.opt_peer_; }
+
 QDC_EXPORT const char* qdc_circuit_set_stream(qdc_circuit* c, void* cuda_stream) {
   c->impl.stream_ = (cudaStream_t)cuda_stream;
   return nullptr;
@@ -117,6 +121,7 @@ QDC_EXPORT const char* qdc_circuit_set_option(qdc_circuit* c, const char* key, l
   else if (strcmp(key, "profile") == 0) c->impl.prof_.on = value != 0;
   else if (strcmp(key, "tile_bits") == 0) c->impl.opt_tile_bits_ = (int)value;
   else if (strcmp(key, "low_bits") == 0) c->impl.opt_low_bits_ = (int)value;
+  else if (strcmp(key, "peer") == 0) c->impl.opt_peer_ = (int)value;  // 0: force the NCCL send/recv exchange
   else if (strcmp(key, "tile_debug") == 0) g_tile_debug = (int)value;  // profiling aid, results invalid when != 0
   else if (strcmp(key, "max_tile_gates") == 0) {
     if (value < 1 || value > QDC_TILE_MAXG_B) return qdc_errf("max_tile_gates must be in 1..%d.", QDC_TILE_MAXG_B);

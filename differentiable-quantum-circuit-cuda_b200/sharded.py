@@ -41,6 +41,11 @@ class ShardedCircuit(Circuit):
         self._h = h
         self._kinds = []
 
+    @property
+    def peer_exchange(self) -> bool:
+        """True when remap exchanges run as the fused NVLink peer-memory swap kernel."""
+        return bool(self._lib.cdll.qdc_circuit_peer_exchange(self._h))
+
     def _allreduce(self, arrays):
         if not arrays:
             return arrays

@@ -63,6 +63,10 @@ const char* qdc_circuit_new(qdc_circuit** out, size_t qubits_number);
 const char* qdc_circuit_new_sharded(qdc_circuit** out, size_t qubits_number, int rank, int world,
                                     const void* nccl_unique_id);
 const char* qdc_nccl_unique_id(void* out128);
+/* 1 if qubit-remap exchanges run as the fused peer-memory swap kernel (partners'
+ * buffers mapped with CUDA IPC over NVLink), 0 if they use NCCL send/recv with
+ * pack / unpack passes (option "peer" = 0 forces the latter). */
+int qdc_circuit_peer_exchange(const qdc_circuit* c);
 const char* qdc_circuit_free(qdc_circuit* c);
 /* Circuit::set_state_from_vector, src/circuit.rs:104-106 */
 const char* qdc_circuit_set_state_from_host(qdc_circuit* c, const qdc_complex* host_state, size_t len);
@@ -99,7 +103,8 @@ const char* qdc_circuit_state_device_ptr(qdc_circuit* c, void** device_ptr);
 const char* qdc_circuit_set_stream(qdc_circuit* c, void* cuda_stream);
 /* Tunables: "fuse" (0 = one pass per instruction, 1 = tiled multi-gate passes),
  * "profile" (1 = time every launch group with CUDA events), "tile_bits",
- * "low_bits", "max_tile_gates" (geometry of the tiled passes; 0 = default). */
+ * "low_bits", "max_tile_gates" (geometry of the tiled passes; 0 = default),
+ * "peer" (sharded: 1 = peer-memory swap kernel, 0 = NCCL send/recv). */
 const char* qdc_circuit_set_option(qdc_circuit* c, const char* key, long value);
 /* Execution statistics of the last run/forward/backward call. */
 typedef struct {

@@ -1,5 +1,5 @@
-"""GPU, world_size > 1: ShardedCircuit (NCCL half-shard exchanges between GPUs of
-one box) must reproduce the single-GPU executor and the oracle.  Needs >= 2
+"""GPU, world_size > 1: ShardedCircuit (half-shard exchanges between GPUs of one box,
+as the NVLink peer-memory swap kernel (peer=1) or NCCL send/recv (peer=0)) must reproduce the single-GPU executor and the oracle.  Needs >= 2
 visible GPUs (`gpurun --gpus 2`); skipped on a single-GPU box."""
 import os
 import socket
@@ -19,7 +19,7 @@ def _ngpus():
         return 0
 
 
-def _worker(rank, world, port, case, n, precision, fuse, q):
+def _worker(rank, world, port, case, n, precision, fuse, peer, q):
     import importlib
     import torch
     import torch.distributed as dist
@@ -37,6 +37,9 @@ def _worker(rank, world, port, case, n, precision, fuse, q):
     c = sharded.ShardedCircuit(n, precision=precision)
     c.set_option("fuse", fuse)
     c.set_option("tile_bits", 11)
+    c.set_option("peer", peer)
+    if peer:
+        assert c.peer_exchange, "CUDA IPC peer mapping failed on an NVLink box"
     for inst in o.instructions:
         c._add(*inst)
     cg, vg = [g.astype(dtype) for g in const], [g.astype(dtype) for g in var]
@@ -56,15 +59,15 @@ def _worker(rank, world, port, case, n, precision, fuse, q):
 @pytest.mark.skipif(_ngpus() < 2, reason="needs >= 2 GPUs")
 @pytest.mark.parametrize("case", ["brickwork", "autodiff", "vqse"])
 @pytest.mark.parametrize("precision", ["f32", "f64"])
-@pytest.mark.parametrize("fuse", [0, 1, 2])
-def test_sharded_matches_oracle(case, precision, fuse):
+@pytest.mark.parametrize("fuse,peer", [(0, 1), (1, 0), (2, 1), (2, 0)])
+def test_sharded_matches_oracle(case, precision, fuse, peer):
     import torch.multiprocessing as mp
     world = 2 if _ngpus() < 4 else 4
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     n = 15
-    procs = [ctx.Process(target=_worker, args=(r, world, port, case, n, precision, fuse, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, case, n, precision, fuse, peer, q)) for r in range(world)]
     for p in procs:
         p.start()
     results = [q.get(timeout=600) for _ in range(world)]
