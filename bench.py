@@ -239,6 +239,10 @@ def run_ours(args):
         circ.set_option("tile_debug", args.tile_debug)
     if world > 1:
         circ.set_option("peer", args.peer)
+    if args.precision == "f32":
+        circ.set_option("soa", args.soa)
+    if args.stagger >= 0:
+        circ.set_option("stagger", args.stagger)
     if args.workload == "vqse":
         n_gates, n_dens = build_vqse(circ, n_total, args.depth)
         var, cts = vqse_inputs(n_total, args.depth, dtype)
@@ -424,6 +428,8 @@ def main():
     ap.add_argument("--low-bits", type=int, default=0, help="L lowest positions forced into every tile (0: default)")
     ap.add_argument("--max-tile-gates", type=int, default=0)
     ap.add_argument("--peer", type=int, default=1, help="sharded: 1 peer-memory swap kernel, 0 NCCL send/recv")
+    ap.add_argument("--soa", type=int, default=1, help="f32 tile kernels: 1 pair-lane smem layout, 0 interleaved layout")
+    ap.add_argument("--stagger", type=int, default=-1, help="CTA start skew, percent of the library default (0: off)")
     ap.add_argument("--tile-debug", type=int, default=0, help="profiling aid (1: no HBM traffic, 2: no gates); invalid results")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -19,6 +19,7 @@ import sys as _sys
 from . import _ffi
 from ._ffi import QdcError, get_lib, lib_path
 from . import common_gates
+from . import state_io
 from .quantized_tensor import QuantizedTensor, get_q1_grad, get_q2_grad, get_q2_grad_diag, data_transfer
 from . import quantum_differentiable_circuit as _qdc_native
 from . import qdc as _qdc_py
@@ -31,5 +32,5 @@ AutoGradCircuit = _qdc_py.AutoGradCircuit
 
 __all__ = [
     "Circuit", "AutoGradCircuit", "QuantizedTensor", "get_q1_grad", "get_q2_grad", "get_q2_grad_diag",
-    "data_transfer", "common_gates", "QdcError", "get_lib", "lib_path",
+    "data_transfer", "common_gates", "state_io", "QdcError", "get_lib", "lib_path",
 ]

@@ -63,6 +63,9 @@ _CIRCUIT_SIGNATURES = {
                                     _sz, c_cplx_p, _sz, C.POINTER(_sz)]),
     "qdc_circuit_copy_state_to_host": (_err, [C.c_void_p, c_cplx_p]),
     "qdc_circuit_state_device_ptr": (_err, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "qdc_circuit_save_state": (_err, [C.c_void_p, C.c_char_p]),
+    "qdc_circuit_load_state": (_err, [C.c_void_p, C.c_char_p]),
+    "qdc_circuit_state_layout": (_err, [C.c_void_p, C.POINTER(C.c_int)]),
     "qdc_circuit_set_stream": (_err, [C.c_void_p, C.c_void_p]),
     "qdc_circuit_set_option": (_err, [C.c_void_p, C.c_char_p, C.c_long]),
     "qdc_circuit_last_stats": (_err, [C.c_void_p, C.c_void_p]),
@@ -92,6 +95,13 @@ class ProfileEntry(C.Structure):
 
 
 def lib_path(precision: str) -> str:
+    # QDC_LIB_VARIANT: development knob -- load lib/libqdc_b200_<precision>_<variant>.so, an experimental
+    # build of the same sources with other -D flags (profiles/scripts/build_variants.py)
+    variant = os.environ.get("QDC_LIB_VARIANT", "")
+    if variant:
+        p = os.path.join(_LIBDIR, f"libqdc_b200_{precision}_{variant}.so")
+        if os.path.exists(p):
+            return p
     return os.path.join(_LIBDIR, f"libqdc_b200_{precision}.so")
 
 

@@ -12,6 +12,7 @@
 //  * the backward step of a gate is one 4*S kernel (engine.cuh) instead of
 //    three 2*S kernels (src/circuit.rs:320-333).
 #pragma once
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -206,7 +207,8 @@ class Circuit {
   std::vector<double> h_res_;
   cudaStream_t stream_ = 0;
   Stats stats_;
-  int opt_fuse_ = 0;
+  int opt_fuse_ = 2;          // 0: one pass per instruction, 1: tiled multi-gate passes, 2: + register-blocked forward
+  int opt_soa_ = 1;           // f32 tile kernels: 1 pair-lane shared-memory layout (tile_soa_kernels.cuh), 0 interleaved
   int opt_tile_bits_ = 0;  // 0: default for the precision
   int opt_low_bits_ = 0;
   int opt_max_tile_gates_ = 24;
@@ -214,6 +216,7 @@ class Circuit {
   qdc::Plan plan_;            // plan of the last forward sweep (backward replays it reversed)
   bool plan_all_dens_ = false;
   std::vector<int> exec_p2_, exec_p1_;  // physical positions each instruction ran at
+  std::vector<int> cur_map_;            // logical qubit -> physical position of state_ right now (empty: identity)
 
   void release() {
     if (state_) cudaFree(state_);
@@ -426,6 +429,119 @@ class Circuit {
       account(1, 0, 0);
     }
     return nullptr;
+  }
+
+  // ------------------------------------------------------- state I/O
+  // Checkpoint format (the reference only has the
+  // in-memory get_cpu_state_copy, src/quantized_tensor.rs:91-99): one file per
+  // rank, 128-byte header + this rank's shard as raw little-endian interleaved
+  // (re, im) pairs in PHYSICAL order (index bit p <-> physical position p).
+  struct StateHeader {
+    char magic[8];        // "QDCSTAT1"
+    uint32_t real_bytes;  // 4 (f32) or 8 (f64)
+    uint32_t n, n_loc, rank, world, reserved;
+    uint8_t map[64];      // logical qubit q -> physical position (0xFF: unused); positions >= n_loc are rank bits
+    uint8_t pad[32];
+  };
+  static_assert(sizeof(StateHeader) == 128, "header layout");
+  static constexpr size_t kIoChunk = (size_t)32 << 20;
+
+  const char* save_state(const char* path) {
+    QDC_TRY(ensure_state());
+    if (n_ > 64) return qdc_errf("state files hold at most 64 qubits.");
+    StateHeader h;
+    memset(&h, 0, sizeof(h));
+    memcpy(h.magic, "QDCSTAT1", 8);
+    h.real_bytes = (uint32_t)sizeof(real_t);
+    h.n = (uint32_t)n_;
+    h.n_loc = (uint32_t)n_loc_;
+    h.rank = (uint32_t)rank_;
+    h.world = (uint32_t)world_;
+    memset(h.map, 0xFF, sizeof(h.map));
+    for (int q = 0; q < n_; q++) h.map[q] = (uint8_t)(cur_map_.empty() ? q : cur_map_[q]);
+    FILE* f = fopen(path, "wb");
+    if (!f) return qdc_errf("cannot open %s for writing.", path);
+    const char* err = nullptr;
+    void* pin[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    auto fail = [&](const char* m) { if (!err) err = m; };
+    if (fwrite(&h, sizeof(h), 1, f) != 1) fail(qdc_errf("short write to %s.", path));
+    for (int k = 0; k < 2 && !err; k++) {
+      if (cudaMallocHost(&pin[k], kIoChunk) != cudaSuccess || cudaEventCreate(&ev[k]) != cudaSuccess)
+        fail(qdc_errf("cannot allocate the pinned staging buffers."));
+    }
+    // double-buffered: the D2H copy of chunk k+1 overlaps the fwrite of chunk k
+    const size_t total = bytes(), nchunks = (total + kIoChunk - 1) / kIoChunk;
+    auto issue = [&](size_t k) {
+      const size_t off = k * kIoChunk, len = std::min(kIoChunk, total - off);
+      if (cudaMemcpyAsync(pin[k & 1], (const char*)state_ + off, len, cudaMemcpyDeviceToHost, stream_) != cudaSuccess ||
+          cudaEventRecord(ev[k & 1], stream_) != cudaSuccess)
+        fail(qdc_errf("CUDA ERROR: device-to-host copy failed in save_state."));
+    };
+    if (!err && nchunks) issue(0);
+    for (size_t k = 0; k < nchunks && !err; k++) {
+      if (k + 1 < nchunks) issue(k + 1);
+      if (err) break;
+      if (cudaEventSynchronize(ev[k & 1]) != cudaSuccess) fail(qdc_errf("CUDA ERROR: save_state copy failed."));
+      const size_t off = k * kIoChunk, len = std::min(kIoChunk, total - off);
+      if (!err && fwrite(pin[k & 1], 1, len, f) != len) fail(qdc_errf("short write to %s.", path));
+    }
+    cudaStreamSynchronize(stream_);
+    for (int k = 0; k < 2; k++) {
+      if (pin[k]) cudaFreeHost(pin[k]);
+      if (ev[k]) cudaEventDestroy(ev[k]);
+    }
+    if (fclose(f) != 0) fail(qdc_errf("cannot close %s.", path));
+    return err;
+  }
+
+  // Load this rank's shard as the INITIAL state of the circuit (the role of
+  // set_state_from_vector).  The file must be in the identity layout.
+  const char* load_state(const char* path) {
+    FILE* f = fopen(path, "rb");
+    if (!f) return qdc_errf("cannot open %s for reading.", path);
+    StateHeader h;
+    const char* err = nullptr;
+    auto fail = [&](const char* m) { if (!err) err = m; };
+    if (fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.magic, "QDCSTAT1", 8) != 0) fail(qdc_errf("%s is not a state file.", path));
+    if (!err && h.real_bytes != sizeof(real_t))
+      fail(qdc_errf("%s holds %u-byte reals, this build uses %zu-byte reals.", path, h.real_bytes, sizeof(real_t)));
+    if (!err && ((int)h.n != n_ || (int)h.n_loc != n_loc_ || (int)h.rank != rank_ || (int)h.world != world_))
+      fail(qdc_errf("%s is shard %u/%u of a %u-qubit state (%u local); this circuit is rank %d/%d of %d qubits (%d local).",
+                    path, h.rank, h.world, h.n, h.n_loc, rank_, world_, n_, n_loc_));
+    for (int q = 0; q < n_ && !err; q++)
+      if (h.map[q] != q) fail(qdc_errf("%s is not in the identity qubit layout; re-save it after backward() or assemble it on the host.", path));
+    void* pin[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    for (int k = 0; k < 2 && !err; k++) {
+      if (cudaMallocHost(&pin[k], kIoChunk) != cudaSuccess || cudaEventCreate(&ev[k]) != cudaSuccess)
+        fail(qdc_errf("cannot allocate the pinned staging buffers."));
+    }
+    if (!err && !initial_ && cudaMalloc((void**)&initial_, bytes()) != cudaSuccess) {
+      initial_ = nullptr;
+      fail(qdc_errf("CUDA ERROR: cannot allocate the initial-state buffer."));
+    }
+    const size_t total = bytes(), nchunks = (total + kIoChunk - 1) / kIoChunk;
+    for (size_t k = 0; k < nchunks && !err; k++) {
+      const size_t off = k * kIoChunk, len = std::min(kIoChunk, total - off);
+      if (k >= 2 && cudaEventSynchronize(ev[k & 1]) != cudaSuccess) fail(qdc_errf("CUDA ERROR: load_state copy failed."));
+      if (!err && fread(pin[k & 1], 1, len, f) != len) fail(qdc_errf("%s is truncated.", path));
+      if (!err && (cudaMemcpyAsync((char*)initial_ + off, pin[k & 1], len, cudaMemcpyHostToDevice, stream_) != cudaSuccess ||
+                   cudaEventRecord(ev[k & 1], stream_) != cudaSuccess))
+        fail(qdc_errf("CUDA ERROR: host-to-device copy failed in load_state."));
+    }
+    if (cudaStreamSynchronize(stream_) != cudaSuccess) fail(qdc_errf("CUDA ERROR: load_state copy failed."));
+    for (int k = 0; k < 2; k++) {
+      if (pin[k]) cudaFreeHost(pin[k]);
+      if (ev[k]) cudaEventDestroy(ev[k]);
+    }
+    fclose(f);
+    return err;
+  }
+
+  // Current layout of the working state: out[q] = physical position of logical qubit q.
+  void state_layout(int* out) const {
+    for (int q = 0; q < n_; q++) out[q] = cur_map_.empty() ? q : cur_map_[q];
   }
 
   // ------------------------------------------------------------ planning
@@ -641,6 +757,7 @@ class Circuit {
     build_plan(all_dens);
     QDC_TRY(reset_state());
     QDC_TRY(run_forward(gp, all_dens));
+    cur_map_ = plan_.final_map;
     // single read-back of every density
     if (nslots) {
       QDC_CUDA(cudaMemcpyAsync(h_res_.data(), d_res_, nslots * 32 * sizeof(double), cudaMemcpyDeviceToHost,
@@ -768,6 +885,7 @@ class Circuit {
         if (kind_is_gate(insts_[i].kind) && kind_is_var(insts_[i].kind)) vslot[i] = s++;
     }
     QDC_TRY(run_backward(gp, dp, vslot));
+    cur_map_.clear();  // every swap has been replayed in reverse: identity layout again
     if (nvar) {
       QDC_CUDA(cudaMemcpyAsync(h_res_.data(), d_res_, nvar * 32 * sizeof(double), cudaMemcpyDeviceToHost,
                                stream_));

@@ -4,6 +4,7 @@
 // ABI (include/qdc_circuit.h).  Everything else has hidden visibility.
 #include "primitives_abi.cuh"
 #include "tile_rb_kernels.cuh"
+#include "tile_soa_kernels.cuh"
 
 struct qdc_circuit {
   Circuit impl;
@@ -101,6 +102,14 @@ QDC_EXPORT const char* qdc_circuit_copy_state_to_host(qdc_circuit* c, cplx_t* ho
   return nullptr;
 }
 
+// Checkpoint of this rank's working state / reload as the initial state (circuit.cuh: state I/O).
+QDC_EXPORT const char* qdc_circuit_save_state(qdc_circuit* c, const char* path) { return c->impl.save_state(path); }
+QDC_EXPORT const char* qdc_circuit_load_state(qdc_circuit* c, const char* path) { return c->impl.load_state(path); }
+QDC_EXPORT const char* qdc_circuit_state_layout(const qdc_circuit* c, int* logical_to_physical) {
+  c->impl.state_layout(logical_to_physical);
+  return nullptr;
+}
+
 QDC_EXPORT const char* qdc_circuit_state_device_ptr(qdc_circuit* c, void** device_ptr) {
   QDC_TRY(c->impl.ensure_state());
   *device_ptr = c->impl.state_;
@@ -121,7 +130,9 @@ QDC_EXPORT const char* qdc_circuit_set_option(qdc_circuit* c, const char* key, l
   else if (strcmp(key, "profile") == 0) c->impl.prof_.on = value != 0;
   else if (strcmp(key, "tile_bits") == 0) c->impl.opt_tile_bits_ = (int)value;
   else if (strcmp(key, "low_bits") == 0) c->impl.opt_low_bits_ = (int)value;
+  else if (strcmp(key, "soa") == 0) c->impl.opt_soa_ = (int)value;    // f32 tile kernels: 0 selects the interleaved-layout kernels
   else if (strcmp(key, "peer") == 0) c->impl.opt_peer_ = (int)value;  // 0: force the NCCL send/recv exchange
+  else if (strcmp(key, "stagger") == 0) g_tile_stagger = (int)value;  // percent of the default CTA start skew (0: off)
   else if (strcmp(key, "tile_debug") == 0) g_tile_debug = (int)value;  // profiling aid, results invalid when != 0
   else if (strcmp(key, "max_tile_gates") == 0) {
     if (value < 1 || value > QDC_TILE_MAXG_B) return qdc_errf("max_tile_gates must be in 1..%d.", QDC_TILE_MAXG_B);

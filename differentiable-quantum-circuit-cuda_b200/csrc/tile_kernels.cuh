@@ -22,6 +22,9 @@
 
 #define QDC_TILE_NT_F 128  // threads per CTA, forward tile kernel (6 CTAs / SM: more independent barrier domains)
 #define QDC_TILE_NT_B 128  // backward tile kernel: fewer threads, more registers each (3 CTAs / SM)
+// default start skew between the CTA waves of an SM, per gate of the pass (~ tile time / resident CTAs)
+#define QDC_STAGGER_NS_PER_GATE_F 800
+#define QDC_STAGGER_NS_PER_GATE_B 1500
 
 #ifdef QDC_F64
 #define QDC_TILE_MAXG_F 48
@@ -64,18 +67,23 @@ struct TileGeo {
   BitDeposit tile;  // tile number (n-T bits)               -> amplitude base
   uint64_t ntiles;
   int debug;  // profiling aid: 1 = skip HBM traffic, 2 = skip the gates (results are then wrong)
+  // De-phasing of the CTAs that share an SM (pair-lane kernels): the k-th of the `resident` CTAs of an SM
+  // starts k * stagger_ns late, so that the SM's CTAs do not fill / drain their tiles in lock-step (convoy:
+  // every CTA of the GPU loading at once is an HBM burst followed by an idle bus while all compute).
+  int nsm, resident, stagger_ns;
 };
 
 enum { TG_Q1 = 0, TG_Q2 = 1, TG_DIAG = 2 };
 
-// Gate matrix as the tile kernels consume it.  f32: pre-packed for the packed
-// FP32 FMA of sm_100 (FFMA2, `fma.rn.f32x2`): A = (re, re), B = (-im, im), so
-// that one complex multiply-accumulate o += g * a is two FFMA2
-//   o = fma2(A, (a.x, a.y), o);  o = fma2(B, (a.y, a.x), o)
-// i.e. half the issue slots of four scalar FFMAs (same pipe throughput,
-// profiles/microbench/ffma2_bench.cu) -- the freed slots absorb the LDS / LDC /
-// integer instructions that made the scalar version issue-bound.
-#ifdef QDC_F64
+// Gate matrix as the tile kernels consume it: plain re / im scalars in the
+// kernel-parameter constant bank.  The gate index is CTA-uniform, so ptxas keeps
+// the entries in UNIFORM registers (LDCU) and feeds them to the packed FP32 FMA
+// of sm_100 (FFMA2, `fma.rn.f32x2`) as broadcast scalars; the swap and the lane
+// negation of the complex product are FFMA2 operand modifiers:
+//   o += g * a   ==   FFMA2 o, a.HI_LO, g.re.F32, o ;  FFMA2 o, -a.LO_HI.NP, g.im.F32, o
+// i.e. two instructions per complex multiply-accumulate and NO operand
+// preparation (the previous pre-packed (re,re)/(-im,im) pairs cost one LDC.64 per
+// two FFMA2 and a pair of MOVs per adjoint element; SASS-checked).
 struct GateMat {
   real_t re[16], im[16];
 };
@@ -87,18 +95,7 @@ static inline void gm_fill(GateMat& m, const real_t* re, const real_t* im) {
     m.im[i] = im[i];
   }
 }
-#else
-struct GateMat {
-  float2 A[16], B[16];
-};
-__host__ __device__ __forceinline__ real_t gm_re(const GateMat& m, int j) { return m.A[j].x; }
-__host__ __device__ __forceinline__ real_t gm_im(const GateMat& m, int j) { return m.B[j].y; }
-static inline void gm_fill(GateMat& m, const real_t* re, const real_t* im) {
-  for (int i = 0; i < 16; i++) {
-    m.A[i] = make_float2(re[i], re[i]);
-    m.B[i] = make_float2(-im[i], im[i]);
-  }
-}
+#ifndef QDC_F64
 __device__ __forceinline__ float2 ffma2(const float2 a, const float2 b, const float2 c) {
   unsigned long long ra = *reinterpret_cast<const unsigned long long*>(&a),
                      rb = *reinterpret_cast<const unsigned long long*>(&b),
@@ -111,6 +108,10 @@ __device__ __forceinline__ float2 fmul2(const float2 a, const float2 b) {
                      rb = *reinterpret_cast<const unsigned long long*>(&b), rd;
   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
   return *reinterpret_cast<float2*>(&rd);
+}
+// o += (gr + i gi) * a
+__device__ __forceinline__ float2 cmac2(const float gr, const float gi, const float2 a, const float2 o) {
+  return ffma2(make_float2(gi, gi), make_float2(-a.y, a.x), ffma2(make_float2(gr, gr), a, o));
 }
 #endif
 
@@ -200,18 +201,13 @@ __device__ __forceinline__ void mv(const GateMat& G, cplx_t (&a)[K]) {
 #pragma unroll
   for (int r = 0; r < K; r++) a[r] = o[r];
 #else
-  float2 as[K], o[K];
-#pragma unroll
-  for (int c = 0; c < K; c++) as[c] = make_float2(a[c].y, a[c].x);
+  float2 o[K];
 #pragma unroll
   for (int r = 0; r < K; r++) {
-    o[r] = fmul2(G.A[r * K], a[0]);
-    o[r] = ffma2(G.B[r * K], as[0], o[r]);
+    o[r] = fmul2(make_float2(G.re[r * K], G.re[r * K]), a[0]);
+    o[r] = ffma2(make_float2(G.im[r * K], G.im[r * K]), make_float2(-a[0].y, a[0].x), o[r]);
 #pragma unroll
-    for (int c = 1; c < K; c++) {
-      o[r] = ffma2(G.A[r * K + c], a[c], o[r]);
-      o[r] = ffma2(G.B[r * K + c], as[c], o[r]);
-    }
+    for (int c = 1; c < K; c++) o[r] = cmac2(G.re[r * K + c], G.im[r * K + c], a[c], o[r]);
   }
 #pragma unroll
   for (int r = 0; r < K; r++) a[r] = o[r];
@@ -224,17 +220,12 @@ __device__ __forceinline__ void outer_tile(const cplx_t (&b)[K], const cplx_t (&
 #ifdef QDC_F64
   outer_acc<K>(b, a, acc);
 #else
-  float2 as[K];
-#pragma unroll
-  for (int q = 0; q < K; q++) as[q] = make_float2(a[q].y, a[q].x);
 #pragma unroll
   for (int p = 0; p < K; p++) {
-    const float2 bb = make_float2(b[p].x, b[p].x), bn = make_float2(-b[p].y, b[p].y);
 #pragma unroll
     for (int q = 0; q < K; q++) {
       float2 t = make_float2(acc[2 * (p * K + q)], acc[2 * (p * K + q) + 1]);
-      t = ffma2(bb, a[q], t);
-      t = ffma2(bn, as[q], t);
+      t = cmac2(b[p].x, b[p].y, a[q], t);
       acc[2 * (p * K + q)] = t.x;
       acc[2 * (p * K + q) + 1] = t.y;
     }
@@ -335,38 +326,29 @@ template <int NT, class Geo>
 __device__ __forceinline__ void tile_rev(vec_t* smf, vec_t* smb, const Geo& geo, int nitems, const TileGateB& G,
                                          real_t* acc) {
   constexpr int K = Geo::K;
-  // phase A: un-compute the state.  Phase B revisits the same items with the
-  // same thread, so no barrier is needed in between; splitting keeps only one
-  // gate matrix live at a time (register pressure).
-  for (int i0 = 0; i0 < nitems; i0 += NT) {  // uniform trip count (nitems % NT == 0): convergent loop
-    const int i = i0 + threadIdx.x;
-    VecU vf[Geo::NVEC];
-    const uint32_t base = geo.base32((uint32_t)i);
-#pragma unroll
-    for (int c = 0; c < Geo::NVEC; c++) vf[c].v = smf[base + geo.off32(c)];
-    cplx_t a[Geo::NG][K];
-    Geo::unpack(vf, a);
-#pragma unroll
-    for (int e = 0; e < Geo::NG; e++) mv<K>(G.inv, a[e]);
-    Geo::pack(vf, a);
-#pragma unroll
-    for (int c = 0; c < Geo::NVEC; c++) smf[base + geo.off32(c)] = vf[c].v;
-  }
-  // phase B: gradient from (pre-gate state, post-gate adjoint), then pull the adjoint back
+  // ONE sweep per gate: un-compute the state, gradient from (pre-gate state, post-gate adjoint), pull
+  // the adjoint back -- 32 B of shared-memory traffic per amplitude instead of the 40 B of separate
+  // un-compute / gradient sweeps (shared bandwidth is 128 B/clk/SM against 128 (64 f64) FMA/clk/SM).
+  // The gate matrices are CTA-uniform kernel parameters (uniform registers), so holding both costs
+  // no vector registers.
   for (int i0 = 0; i0 < nitems; i0 += NT) {  // uniform trip count (nitems % NT == 0): convergent loop
     const int i = i0 + threadIdx.x;
     VecU vf[Geo::NVEC], vb[Geo::NVEC];
     const uint32_t base = geo.base32((uint32_t)i);
 #pragma unroll
     for (int c = 0; c < Geo::NVEC; c++) {
+      vf[c].v = smf[base + geo.off32(c)];
       vb[c].v = smb[base + geo.off32(c)];
-      if (G.slot >= 0) vf[c].v = smf[base + geo.off32(c)];
     }
-    cplx_t b[Geo::NG][K];
+    cplx_t a[Geo::NG][K], b[Geo::NG][K];
+    Geo::unpack(vf, a);
     Geo::unpack(vb, b);
+#pragma unroll
+    for (int e = 0; e < Geo::NG; e++) mv<K>(G.inv, a[e]);
+    Geo::pack(vf, a);
+#pragma unroll
+    for (int c = 0; c < Geo::NVEC; c++) smf[base + geo.off32(c)] = vf[c].v;
     if (G.slot >= 0) {
-      cplx_t a[Geo::NG][K];
-      Geo::unpack(vf, a);
 #pragma unroll
       for (int e = 0; e < Geo::NG; e++) outer_tile<K>(b[e], a[e], acc);
     }
@@ -508,10 +490,32 @@ __global__ void k_tile_final(const double* __restrict__ partials, int ncta, int 
 }
 
 // ------------------------------------------------------------ host launch
+#ifndef QDC_F64
+// pair-lane layout kernels (tile_soa_kernels.cuh), the f32 default
+__global__ void __launch_bounds__(QDC_TILE_NT_F, 6)
+    k_tile_fwd_soa(cplx_t* __restrict__ state, const __grid_constant__ TileFwdParams p);
+__global__ void __launch_bounds__(QDC_TILE_NT_B, 3)
+    k_tile_bwd_soa(cplx_t* __restrict__ fwd, cplx_t* __restrict__ bwd, const __grid_constant__ TileBwdParams p,
+                   double* __restrict__ partials);
+#define QDC_KFWD (opt_soa_ ? k_tile_fwd_soa : k_tile_fwd)
+#define QDC_KBWD (opt_soa_ ? k_tile_bwd_soa : k_tile_bwd)
+#else
+#define QDC_KFWD k_tile_fwd
+#define QDC_KBWD k_tile_bwd
+#endif
 static int g_tile_debug = 0;
+static int g_tile_stagger = 0;  // option "stagger": percent of the default start skew per gate of the pass.
+                                // Off by default: measured no gain (28 q: 558.2 vs 558.2 ms/step at 0 / 100 %), i.e. no convoy.
 static inline const char* make_tile_geo(const qdc::Plan& plan, const qdc::Step& t, int n_loc, int low_bits,
                                         TileGeo* geo, std::vector<int>* tile_pos_of) {
   geo->debug = g_tile_debug;
+  geo->stagger_ns = 0;
+  geo->resident = 1;
+  {
+    DeviceInfo di;
+    QDC_TRY(qdc_device_info(&di));
+    geo->nsm = di.sm_count;
+  }
   std::vector<int> bits(plan.tile_bits.begin() + t.tb_first, plan.tile_bits.begin() + t.tb_first + t.tb_count);
   // pad with the lowest unused positions so that T >= log2(threads * vector) and runs stay whole
   int T = (int)bits.size();
@@ -616,10 +620,12 @@ inline const char* Circuit::run_tile_forward(const qdc::Step& t, const std::vect
   }
   const size_t smem = sizeof(cplx_t) << p.geo.T;
   int grid = 0;
-  QDC_TRY(tile_grid((const void*)k_tile_fwd, QDC_TILE_NT_F, smem, p.geo.ntiles, &grid));
+  QDC_TRY(tile_grid((const void*)QDC_KFWD, QDC_TILE_NT_F, smem, p.geo.ntiles, &grid));
+  p.geo.resident = (grid + p.geo.nsm - 1) / p.geo.nsm;
+  p.geo.stagger_ns = g_tile_stagger * t.count * QDC_STAGGER_NS_PER_GATE_F / 100;
   cudaEvent_t pa = nullptr;
   if (prof_.on) pa = prof_.begin(stream_);
-  k_tile_fwd<<<grid, QDC_TILE_NT_F, smem, stream_>>>(state_, p);
+  QDC_KFWD<<<grid, QDC_TILE_NT_F, smem, stream_>>>(state_, p);
   QDC_CUDA(cudaGetLastError());
   if (prof_.on) prof_.end(stream_, CAT_TILE_FWD, pa, 2ull * t.count * bytes());
   stats_.kernel_launches += 1;
@@ -654,10 +660,12 @@ inline const char* Circuit::run_tile_backward(const qdc::Step& t, const std::vec
     }
     const size_t smem = sizeof(cplx_t) << p.geo.T;
     int grid = 0;
-    QDC_TRY(tile_grid((const void*)k_tile_fwd, QDC_TILE_NT_F, smem, p.geo.ntiles, &grid));
+    QDC_TRY(tile_grid((const void*)QDC_KFWD, QDC_TILE_NT_F, smem, p.geo.ntiles, &grid));
+    p.geo.resident = (grid + p.geo.nsm - 1) / p.geo.nsm;
+  p.geo.stagger_ns = g_tile_stagger * t.count * QDC_STAGGER_NS_PER_GATE_F / 100;
     cudaEvent_t pa = nullptr;
     if (prof_.on) pa = prof_.begin(stream_);
-    k_tile_fwd<<<grid, QDC_TILE_NT_F, smem, stream_>>>(state_, p);
+    QDC_KFWD<<<grid, QDC_TILE_NT_F, smem, stream_>>>(state_, p);
     QDC_CUDA(cudaGetLastError());
     if (prof_.on) prof_.end(stream_, CAT_UNCOMPUTE, pa, 2ull * t.count * bytes());
     stats_.kernel_launches += 1;
@@ -693,7 +701,9 @@ inline const char* Circuit::run_tile_backward(const qdc::Step& t, const std::vec
   const size_t smem = 2 * tile_bytes + QDC_TILE_MAXG_B * 32 * sizeof(double) +
                       2 * (QDC_TILE_NT_B / 32) * 32 * sizeof(real_t);
   int grid = 0;
-  QDC_TRY(tile_grid((const void*)k_tile_bwd, QDC_TILE_NT_B, smem, p.geo.ntiles, &grid));
+  QDC_TRY(tile_grid((const void*)QDC_KBWD, QDC_TILE_NT_B, smem, p.geo.ntiles, &grid));
+  p.geo.resident = (grid + p.geo.nsm - 1) / p.geo.nsm;
+  p.geo.stagger_ns = g_tile_stagger * t.count * QDC_STAGGER_NS_PER_GATE_B / 100;
   const size_t need = (size_t)grid * QDC_TILE_MAXG_B * 32;
   if (need > tile_partials_cap_) {
     if (tile_partials_) QDC_CUDA(cudaFree(tile_partials_));
@@ -702,7 +712,7 @@ inline const char* Circuit::run_tile_backward(const qdc::Step& t, const std::vec
   }
   cudaEvent_t pa = nullptr;
   if (prof_.on) pa = prof_.begin(stream_);
-  k_tile_bwd<<<grid, QDC_TILE_NT_B, smem, stream_>>>(state_, bwd_, p, tile_partials_);
+  QDC_KBWD<<<grid, QDC_TILE_NT_B, smem, stream_>>>(state_, bwd_, p, tile_partials_);
   QDC_CUDA(cudaGetLastError());
   k_tile_final<<<t.count, 32, 0, stream_>>>(tile_partials_, grid, t.count, h_slots, d_res_);
   QDC_CUDA(cudaGetLastError());

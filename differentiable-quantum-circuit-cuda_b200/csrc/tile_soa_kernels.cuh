@@ -1,0 +1,454 @@
+// Tiled multi-gate passes, f32, "pair-lane" shared-memory layout.
+//
+// Same tiling / parameters / host code as tile_kernels.cuh, but the tile is
+// held in shared memory with the two amplitudes of a 128-bit vector
+// de-interleaved:
+//
+//   HBM   float4 = (re0, im0, re1, im1)      amplitudes 2v, 2v+1 (tile bit 0)
+//   smem  float4 = (re0, re1, im0, im1)      the swap is done in registers by tile_io
+//
+// A gate that does not act on tile bit 0 treats the two amplitudes of a vector
+// identically, so (re0, re1) and (im0, im1) are the two lanes of the packed FP32
+// FMA of sm_100 (FFMA2) and a complex multiply-accumulate with a CTA-uniform
+// gate entry g is
+//
+//   o.re += g.re * a.re ; o.re += (-g.im) * a.im ; o.im += g.re * a.im ; o.im += g.im * a.re
+//
+// = 4 FFMA2 for two amplitudes with the gate entry as a broadcast UNIFORM-register
+// operand (LDCU from the kernel-parameter bank) and negation as an operand
+// modifier: no swaps, no pre-packed constants, no MOVs.  SASS of the inner loops
+// (cuobjdump): forward 64 packed math + 4 LDS.128 + 4 STS.128 + ~20
+// others per item (was 64 + ~60); reverse 192 + 8 + 8 + ~40 (was 192 + ~195).
+// The gradient outer product accumulates per lane (acc.re / acc.im pairs) and the
+// lanes are folded once per gate, before the warp reduce-scatter.
+//
+// The reverse pass is ONE sweep per gate (un-compute, gradient, adjoint pull-back
+// on the same registers): shared-memory traffic 32 B per amplitude per gate
+// instead of 40 B -- at 128 B/clk/SM shared bandwidth vs 128 FMA/clk/SM the two
+// sweeps of the older kernel were as expensive as its FMAs.
+//
+// Gates that DO act on tile bit 0 (physical qubit 0 only) mix the lanes; they are
+// unpacked to (re, im) pairs and go through the complex helpers of
+// tile_kernels.cuh (rare: 1 in n-1 brickwork gates).
+#pragma once
+#include "tile_kernels.cuh"
+
+#ifndef QDC_F64
+
+struct V4 {
+  float2 re, im;  // (lane 0, lane 1)
+};
+__device__ __forceinline__ V4 ld4(const vec_t* p) {
+  const float4 t = *p;
+  V4 v;
+  v.re = make_float2(t.x, t.y);
+  v.im = make_float2(t.z, t.w);
+  return v;
+}
+__device__ __forceinline__ void st4(vec_t* p, const V4& v) { *p = make_float4(v.re.x, v.re.y, v.im.x, v.im.y); }
+__device__ __forceinline__ float2 bc2(const float x) { return make_float2(x, x); }
+__device__ __forceinline__ float2 neg2(const float2 a) { return make_float2(-a.x, -a.y); }
+
+// o = G a for both lanes; G is CTA-uniform
+template <int K>
+__device__ __forceinline__ void mv_soa(const GateMat& G, const V4 (&a)[K], V4 (&o)[K]) {
+#pragma unroll
+  for (int r = 0; r < K; r++) {
+    o[r].re = fmul2(bc2(G.re[r * K]), a[0].re);
+    o[r].im = fmul2(bc2(G.re[r * K]), a[0].im);
+    o[r].re = ffma2(bc2(-G.im[r * K]), a[0].im, o[r].re);
+    o[r].im = ffma2(bc2(G.im[r * K]), a[0].re, o[r].im);
+#pragma unroll
+    for (int c = 1; c < K; c++) {
+      o[r].re = ffma2(bc2(G.re[r * K + c]), a[c].re, o[r].re);
+      o[r].im = ffma2(bc2(G.re[r * K + c]), a[c].im, o[r].im);
+      o[r].re = ffma2(bc2(-G.im[r * K + c]), a[c].im, o[r].re);
+      o[r].im = ffma2(bc2(G.im[r * K + c]), a[c].re, o[r].im);
+    }
+  }
+}
+
+// per-lane accumulation of b[p] * a[q] (no conjugation)
+template <int K>
+__device__ __forceinline__ void outer_soa(const V4 (&b)[K], const V4 (&a)[K], float2 (&are)[16], float2 (&aim)[16]) {
+#pragma unroll
+  for (int p = 0; p < K; p++) {
+    const float2 nbi = neg2(b[p].im);
+#pragma unroll
+    for (int q = 0; q < K; q++) {
+      are[p * K + q] = ffma2(b[p].re, a[q].re, are[p * K + q]);
+      are[p * K + q] = ffma2(nbi, a[q].im, are[p * K + q]);
+      aim[p * K + q] = ffma2(b[p].re, a[q].im, aim[p * K + q]);
+      aim[p * K + q] = ffma2(b[p].im, a[q].re, aim[p * K + q]);
+    }
+  }
+}
+
+// ------------------------------------------------------------ tile <-> HBM
+// Batches of QDC_TILE_IO_UNR independent 128-bit accesses per thread.  (Issuing all 16 loads of a
+// 2^12 tile at once was measured and is NOT faster -- 576 vs 561 ms/step at 28 q -- the tile fill of
+// one CTA hides behind the other CTAs' math; it only costs registers.)
+#ifndef QDC_TILE_IO_UNR
+#define QDC_TILE_IO_UNR 4
+#endif
+template <int NT, bool LOAD>
+__device__ __forceinline__ void tile_io_soa(vec_t* __restrict__ gmem, vec_t* __restrict__ smv, const TileAddr<NT>& ta,
+                                            uint64_t tile_base_vec) {
+  const uint64_t base = tile_base_vec + ta.lo;
+  const int tid = threadIdx.x;
+  constexpr int UNR = QDC_TILE_IO_UNR;
+#pragma unroll
+  for (int i0 = 0; i0 < TileAddr<NT>::MAXI; i0 += UNR) {
+    if (i0 < ta.niter) {
+      vec_t tmp[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; u++) {
+        if (LOAD) tmp[u] = gmem[base + ((uint64_t)ta.it[i0 + u] << ta.runv_log)];
+        else tmp[u] = smv[tid + (i0 + u) * NT];
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; u++) {
+        const vec_t s = make_float4(tmp[u].x, tmp[u].z, tmp[u].y, tmp[u].w);  // (re0,im0,re1,im1) <-> (re0,re1,im0,im1)
+        if (LOAD) smv[tid + (i0 + u) * NT] = s;
+        else gmem[base + ((uint64_t)ta.it[i0 + u] << ta.runv_log)] = s;
+      }
+    }
+  }
+}
+
+// L2 prefetch of a tile this CTA will load later (its next tile): one
+// `prefetch.global.L2` per 128-byte line, issued by the thread that will load the
+// line's first vector.  Costs no registers or shared memory (a double-buffered
+// smem prefetch would halve the resident CTAs); the later fill then pays L2
+// latency instead of HBM latency.  ncu (profiles/r1_tile_bwd_soa_28q_ncu.txt):
+// 36 % of the reverse kernel's warp samples sat in the per-tile fill / drain code --
+// but that wait is hidden behind the SM's other CTAs: measured gain 0.5 % (28 q, depth
+// 40: 558.9 -> 555.7 ms/step), so the prefetch is compiled out by default.
+#ifndef QDC_TILE_PREFETCH
+#define QDC_TILE_PREFETCH 0
+#endif
+template <int NT>
+__device__ __forceinline__ void tile_prefetch_l2(const vec_t* __restrict__ gmem, const TileAddr<NT>& ta,
+                                                 uint64_t tile_base_vec) {
+#if QDC_TILE_PREFETCH
+  if ((threadIdx.x & 7) == 0) {  // 8 vectors = 128 bytes; runs are >= 128-byte aligned
+    const vec_t* p = gmem + tile_base_vec + ta.lo;
+#pragma unroll
+    for (int i = 0; i < TileAddr<NT>::MAXI; i++)
+      if (i < ta.niter) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + ((uint64_t)ta.it[i] << ta.runv_log)));
+  }
+#endif
+}
+
+// start skew of the CTAs sharing an SM (see TileGeo::stagger_ns): the k-th CTA to arrive on an SM
+// (arrival counter per %smid, never reset: only the order modulo the resident CTAs matters) starts
+// (k mod resident) * stagger_ns late.
+__device__ unsigned g_sm_arrivals[1024];
+__device__ __forceinline__ void tile_stagger(const TileGeo& geo) {
+  if (geo.stagger_ns > 0) {
+    if (threadIdx.x == 0) {
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      const unsigned k = atomicAdd(&g_sm_arrivals[smid & 1023u], 1u) % (unsigned)geo.resident;
+      for (unsigned left = k * (unsigned)geo.stagger_ns; left > 0;) {
+        const unsigned d = left > 500000u ? 500000u : left;
+        __nanosleep(d);
+        left -= d;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------- forward
+template <int NT, class Geo>
+__device__ __forceinline__ void tile_apply_soa(vec_t* smv, const Geo& geo, int nitems, const GateMat& G) {
+  constexpr int K = Geo::K;
+  for (int i0 = 0; i0 < nitems; i0 += NT) {  // uniform trip count (nitems % NT == 0)
+    const uint32_t base = geo.base32((uint32_t)(i0 + threadIdx.x));
+    V4 a[K], o[K];
+#pragma unroll
+    for (int c = 0; c < K; c++) a[c] = ld4(smv + base + geo.off32(c));
+    mv_soa<K>(G, a, o);
+#pragma unroll
+    for (int c = 0; c < K; c++) st4(smv + base + geo.off32(c), o[c]);
+  }
+}
+
+// gate on tile bit 0 (lane-mixing): K = 4: bits (hv + 1, 0), two vectors; K = 2: bit 0, one vector
+template <int K>
+__device__ __forceinline__ void unpack_lane_mix(const V4 (&v)[K / 2], cplx_t (&a)[K]) {
+#pragma unroll
+  for (int h = 0; h < K / 2; h++) {
+    a[2 * h] = make_float2(v[h].re.x, v[h].im.x);
+    a[2 * h + 1] = make_float2(v[h].re.y, v[h].im.y);
+  }
+}
+template <int K>
+__device__ __forceinline__ void pack_lane_mix(V4 (&v)[K / 2], const cplx_t (&a)[K]) {
+#pragma unroll
+  for (int h = 0; h < K / 2; h++) {
+    v[h].re = make_float2(a[2 * h].x, a[2 * h + 1].x);
+    v[h].im = make_float2(a[2 * h].y, a[2 * h + 1].y);
+  }
+}
+
+template <int NT, int K>
+__device__ __forceinline__ void tile_apply_mix(vec_t* smv, int hv, int nitems, const GateMat& G) {
+  for (int i0 = 0; i0 < nitems; i0 += NT) {
+    const uint32_t i = (uint32_t)(i0 + threadIdx.x);
+    const uint32_t base = (K == 4) ? ins0_32(i, hv) : i;
+    V4 v[K / 2];
+#pragma unroll
+    for (int h = 0; h < K / 2; h++) v[h] = ld4(smv + base + ((uint32_t)h << hv));
+    cplx_t a[K];
+    unpack_lane_mix<K>(v, a);
+    mv<K>(G, a);
+    pack_lane_mix<K>(v, a);
+#pragma unroll
+    for (int h = 0; h < K / 2; h++) st4(smv + base + ((uint32_t)h << hv), v[h]);
+  }
+}
+
+// per-lane diagonal entries of vector i: lane e is amplitude 2 i + e
+__device__ __forceinline__ void diag_lanes(const GateMat& D, int i, int a, int b, float2& dr, float2& di, int& j0, int& j1) {
+  const int amp = 2 * i;
+  j0 = 2 * ((amp >> a) & 1) + ((amp >> b) & 1);
+  j1 = 2 * (((amp + 1) >> a) & 1) + (((amp + 1) >> b) & 1);
+  dr = make_float2(gm_sel4_re(D, j0), gm_sel4_re(D, j1));
+  di = make_float2(gm_sel4_im(D, j0), gm_sel4_im(D, j1));
+}
+
+template <int NT>
+__device__ __forceinline__ void tile_diag_soa(vec_t* smv, int nvec, const GateMat& D, int a, int b) {
+  for (int i0 = 0; i0 < nvec; i0 += NT) {
+    const int i = i0 + threadIdx.x;
+    float2 dr, di;
+    int j0, j1;
+    diag_lanes(D, i, a, b, dr, di, j0, j1);
+    V4 v = ld4(smv + i), o;
+    o.re = ffma2(neg2(v.im), di, fmul2(v.re, dr));
+    o.im = ffma2(v.im, dr, fmul2(v.re, di));
+    st4(smv + i, o);
+  }
+}
+
+__global__ void __launch_bounds__(QDC_TILE_NT_F, 6)
+    k_tile_fwd_soa(cplx_t* __restrict__ state, const __grid_constant__ TileFwdParams p) {
+  extern __shared__ __align__(16) unsigned char tile_smem[];
+  vec_t* smv = (vec_t*)tile_smem;
+  const int nvec = 1 << (p.geo.T - QDC_LV);
+  TileAddr<QDC_TILE_NT_F> ta;
+  ta.init(p.geo);
+  tile_stagger(p.geo);
+  for (uint64_t tile = blockIdx.x; tile < p.geo.ntiles; tile += gridDim.x) {
+    const uint64_t tbase = p.geo.tile(tile) >> QDC_LV;
+    if (p.geo.debug != 1) tile_io_soa<QDC_TILE_NT_F, true>((vec_t*)state, smv, ta, tbase);
+    if (tile + gridDim.x < p.geo.ntiles && p.geo.debug != 1)
+      tile_prefetch_l2<QDC_TILE_NT_F>((const vec_t*)state, ta, p.geo.tile(tile + gridDim.x) >> QDC_LV);
+    __syncthreads();
+    for (int g = 0; g < (p.geo.debug == 2 ? 0 : p.ngates); g++) {
+      const TileGateF& G = p.g[g];
+      if (G.type == TG_Q2) {
+        if (G.b == 0) {
+          tile_apply_mix<QDC_TILE_NT_F, 4>(smv, G.a - 1, nvec / 2, G.m);
+        } else {
+          GeoQ2HH geo;
+          geo.lv = G.b - QDC_LV;
+          geo.hv = G.a - QDC_LV;
+          tile_apply_soa<QDC_TILE_NT_F>(smv, geo, nvec / 4, G.m);
+        }
+      } else if (G.type == TG_Q1) {
+        if (G.a == 0) {
+          tile_apply_mix<QDC_TILE_NT_F, 2>(smv, 0, nvec, G.m);
+        } else {
+          GeoQ1H geo;
+          geo.pv = G.a - QDC_LV;
+          tile_apply_soa<QDC_TILE_NT_F>(smv, geo, nvec / 2, G.m);
+        }
+      } else {
+        tile_diag_soa<QDC_TILE_NT_F>(smv, nvec, G.m, G.a, G.b);
+      }
+      __syncthreads();
+    }
+    if (p.geo.debug != 1) tile_io_soa<QDC_TILE_NT_F, false>((vec_t*)state, smv, ta, tbase);
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------- reverse
+template <int NT, class Geo>
+__device__ __forceinline__ void tile_rev_soa(vec_t* smf, vec_t* smb, const Geo& geo, int nitems, const TileGateB& G,
+                                             real_t (&acc)[32]) {
+  constexpr int K = Geo::K;
+  float2 are[16], aim[16];
+#pragma unroll
+  for (int k = 0; k < 16; k++) are[k] = aim[k] = make_float2(0.f, 0.f);
+  for (int i0 = 0; i0 < nitems; i0 += NT) {  // uniform trip count
+    const uint32_t base = geo.base32((uint32_t)(i0 + threadIdx.x));
+    V4 f[K], a[K], b[K], bo[K];
+#pragma unroll
+    for (int c = 0; c < K; c++) {
+      f[c] = ld4(smf + base + geo.off32(c));
+      b[c] = ld4(smb + base + geo.off32(c));
+    }
+    mv_soa<K>(G.inv, f, a);                               // un-compute the state
+#pragma unroll
+    for (int c = 0; c < K; c++) st4(smf + base + geo.off32(c), a[c]);
+    if (G.slot >= 0) outer_soa<K>(b, a, are, aim);        // gradient from (pre-gate state, post-gate adjoint)
+    mv_soa<K>(G.tr, b, bo);                               // pull the adjoint back
+#pragma unroll
+    for (int c = 0; c < K; c++) st4(smb + base + geo.off32(c), bo[c]);
+  }
+#pragma unroll
+  for (int k = 0; k < K * K; k++) {
+    acc[2 * k] = are[k].x + are[k].y;
+    acc[2 * k + 1] = aim[k].x + aim[k].y;
+  }
+}
+
+template <int NT, int K>
+__device__ __forceinline__ void tile_rev_mix(vec_t* smf, vec_t* smb, int hv, int nitems, const TileGateB& G,
+                                             real_t (&acc)[32]) {
+  for (int i0 = 0; i0 < nitems; i0 += NT) {
+    const uint32_t i = (uint32_t)(i0 + threadIdx.x);
+    const uint32_t base = (K == 4) ? ins0_32(i, hv) : i;
+    V4 vf[K / 2], vb[K / 2];
+#pragma unroll
+    for (int h = 0; h < K / 2; h++) {
+      vf[h] = ld4(smf + base + ((uint32_t)h << hv));
+      vb[h] = ld4(smb + base + ((uint32_t)h << hv));
+    }
+    cplx_t a[K], b[K];
+    unpack_lane_mix<K>(vf, a);
+    unpack_lane_mix<K>(vb, b);
+    mv<K>(G.inv, a);
+    if (G.slot >= 0) outer_tile<K>(b, a, acc);
+    mv<K>(G.tr, b);
+    pack_lane_mix<K>(vf, a);
+    pack_lane_mix<K>(vb, b);
+#pragma unroll
+    for (int h = 0; h < K / 2; h++) {
+      st4(smf + base + ((uint32_t)h << hv), vf[h]);
+      st4(smb + base + ((uint32_t)h << hv), vb[h]);
+    }
+  }
+}
+
+template <int NT>
+__device__ __forceinline__ void tile_rev_diag_soa(vec_t* smf, vec_t* smb, int nvec, const TileGateB& G,
+                                                  real_t (&acc)[32]) {
+  for (int i0 = 0; i0 < nvec; i0 += NT) {
+    const int i = i0 + threadIdx.x;
+    float2 ir, ii, dr, di;
+    int j0, j1;
+    diag_lanes(G.inv, i, G.a, G.b, ir, ii, j0, j1);
+    diag_lanes(G.tr, i, G.a, G.b, dr, di, j0, j1);
+    const V4 f = ld4(smf + i), b = ld4(smb + i);
+    V4 fo, bo;
+    fo.re = ffma2(neg2(f.im), ii, fmul2(f.re, ir));
+    fo.im = ffma2(f.im, ir, fmul2(f.re, ii));
+    if (G.slot >= 0) {
+      const float2 pr = ffma2(neg2(b.im), fo.im, fmul2(b.re, fo.re));
+      const float2 pi = ffma2(b.im, fo.re, fmul2(b.re, fo.im));
+#pragma unroll
+      for (int jj = 0; jj < 4; jj++) {
+        acc[2 * jj] += ((j0 == jj) ? pr.x : 0.f) + ((j1 == jj) ? pr.y : 0.f);
+        acc[2 * jj + 1] += ((j0 == jj) ? pi.x : 0.f) + ((j1 == jj) ? pi.y : 0.f);
+      }
+    }
+    bo.re = ffma2(neg2(b.im), di, fmul2(b.re, dr));
+    bo.im = ffma2(b.im, dr, fmul2(b.re, di));
+    st4(smf + i, fo);
+    st4(smb + i, bo);
+  }
+}
+
+// partials: [gridDim.x][ngates][32] doubles (same contract as k_tile_bwd)
+__global__ void __launch_bounds__(QDC_TILE_NT_B, 3)
+    k_tile_bwd_soa(cplx_t* __restrict__ fwd, cplx_t* __restrict__ bwd, const __grid_constant__ TileBwdParams p,
+                   double* __restrict__ partials) {
+  extern __shared__ __align__(16) unsigned char tile_smem[];
+  const int nvec = 1 << (p.geo.T - QDC_LV);
+  vec_t* smf = (vec_t*)tile_smem;
+  vec_t* smb = smf + nvec;
+  double* sm_acc = (double*)(smb + nvec);                    // [MAXG_B][32]
+  real_t* sm_part = (real_t*)(sm_acc + QDC_TILE_MAXG_B * 32);  // [2][warps][32]
+  constexpr int NW = QDC_TILE_NT_B / 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < QDC_TILE_MAXG_B * 32; i += QDC_TILE_NT_B) sm_acc[i] = 0.0;
+  __syncthreads();
+  TileAddr<QDC_TILE_NT_B> ta;
+  ta.init(p.geo);
+  tile_stagger(p.geo);
+  for (uint64_t tile = blockIdx.x; tile < p.geo.ntiles; tile += gridDim.x) {
+    const uint64_t tbase = p.geo.tile(tile) >> QDC_LV;
+    if (p.geo.debug != 1) {
+      tile_io_soa<QDC_TILE_NT_B, true>((vec_t*)fwd, smf, ta, tbase);
+      tile_io_soa<QDC_TILE_NT_B, true>((vec_t*)bwd, smb, ta, tbase);
+      if (tile + gridDim.x < p.geo.ntiles) {
+        const uint64_t nbase = p.geo.tile(tile + gridDim.x) >> QDC_LV;
+        tile_prefetch_l2<QDC_TILE_NT_B>((const vec_t*)fwd, ta, nbase);
+        tile_prefetch_l2<QDC_TILE_NT_B>((const vec_t*)bwd, ta, nbase);
+      }
+    }
+    __syncthreads();
+    for (int g = 0; g < (p.geo.debug == 2 ? 0 : p.ngates); g++) {
+      const TileGateB& G = p.g[g];
+      real_t acc[32];
+#pragma unroll
+      for (int k = 0; k < 32; k++) acc[k] = 0;
+      if (G.type == TG_Q2) {
+        if (G.b == 0) {
+          tile_rev_mix<QDC_TILE_NT_B, 4>(smf, smb, G.a - 1, nvec / 2, G, acc);
+        } else {
+          GeoQ2HH geo;
+          geo.lv = G.b - QDC_LV;
+          geo.hv = G.a - QDC_LV;
+          tile_rev_soa<QDC_TILE_NT_B>(smf, smb, geo, nvec / 4, G, acc);
+        }
+      } else if (G.type == TG_Q1) {
+        if (G.a == 0) {
+          tile_rev_mix<QDC_TILE_NT_B, 2>(smf, smb, 0, nvec, G, acc);
+        } else {
+          GeoQ1H geo;
+          geo.pv = G.a - QDC_LV;
+          tile_rev_soa<QDC_TILE_NT_B>(smf, smb, geo, nvec / 2, G, acc);
+        }
+      } else {
+        tile_rev_diag_soa<QDC_TILE_NT_B>(smf, smb, nvec, G, acc);
+      }
+      real_t* part = sm_part + (size_t)(g & 1) * NW * 32;
+#ifdef QDC_EXPERIMENT_NO_FLUSH  // timing experiment only (gradients wrong): cost of the per-gate reduction
+      if (G.slot >= 0) {
+        real_t t = 0;
+#pragma unroll
+        for (int k = 0; k < 32; k++) t += acc[k];
+        if (t == 12345.f) part[warp * 32 + lane] = t;
+      }
+#else
+      if (G.slot >= 0) {
+        double d = 0.0;
+        warp_flush<32>(acc, d, lane);  // lane j now holds the warp total of value j
+        part[warp * 32 + lane] = (real_t)d;
+      }
+#endif
+      __syncthreads();
+      if (G.slot >= 0 && warp == 0) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < NW; w++) s += (double)part[w * 32 + lane];
+        sm_acc[g * 32 + lane] += s;
+      }
+    }
+    if (p.geo.debug != 1) {
+      tile_io_soa<QDC_TILE_NT_B, false>((vec_t*)fwd, smf, ta, tbase);
+      tile_io_soa<QDC_TILE_NT_B, false>((vec_t*)bwd, smb, ta, tbase);
+    }
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < p.ngates * 32; i += QDC_TILE_NT_B)
+    partials[(size_t)blockIdx.x * p.ngates * 32 + i] = sm_acc[i];
+}
+
+#endif  // !QDC_F64

@@ -154,6 +154,20 @@ class Circuit:
         self._lib.call("qdc_circuit_copy_state_to_host", self._h, out.ctypes.data)
         return out
 
+    def save_state(self, path: str):
+        """Stream this rank's working state to `path` (format: include/qdc_circuit.h, `state_io.read_state`)."""
+        self._lib.call("qdc_circuit_save_state", self._h, str(path).encode())
+
+    def load_state(self, path: str):
+        """Install the state file `path` (identity layout) as the initial state, like set_state_from_vector."""
+        self._lib.call("qdc_circuit_load_state", self._h, str(path).encode())
+
+    def state_layout(self) -> List[int]:
+        """Physical position of every logical qubit in the working state (identity unless sharded mid-sweep)."""
+        out = (C.c_int * self.qubits_number)()
+        self._lib.call("qdc_circuit_state_layout", self._h, out)
+        return list(out)
+
     def set_option(self, key: str, value: int):
         self._lib.call("qdc_circuit_set_option", self._h, key.encode(), int(value))
 

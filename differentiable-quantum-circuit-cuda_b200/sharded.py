@@ -77,6 +77,13 @@ class ShardedCircuit(Circuit):
     def backward(self, grads_wrt_density, const_gates, var_gates):
         return self._allreduce(super().backward(grads_wrt_density, const_gates, var_gates))
 
+    def save_state(self, path: str):
+        """One file per rank: `path` with ".rank{r}of{w}" appended (state_io.assemble re-joins them)."""
+        super().save_state(f"{path}.rank{self.rank}of{self.world}")
+
+    def load_state(self, path: str):
+        super().load_state(f"{path}.rank{self.rank}of{self.world}")
+
     def get_cpu_state_copy(self):
         """This rank's shard in the current physical layout (2^(n - g) entries)."""
         out = np.empty(1 << self.local_qubits, dtype=self._lib.cdtype)

@@ -97,6 +97,19 @@ const char* qdc_circuit_backward(qdc_circuit* c,
 /* QuantizedTensor::get_cpu_state_copy on the circuit's working state,
  * src/quantized_tensor.rs:91-99 (2^n entries). */
 const char* qdc_circuit_copy_state_to_host(qdc_circuit* c, qdc_complex* host_state);
+/* State I/O (no reference counterpart beyond
+ * get_cpu_state_copy).  One file per rank: a 128-byte header
+ *   char magic[8] = "QDCSTAT1"; u32 real_bytes (4|8), n, n_loc, rank, world, reserved;
+ *   u8 map[64] (logical qubit -> physical position, 0xFF unused); u8 pad[32]
+ * followed by the rank's shard, 2^n_loc raw little-endian interleaved (re, im)
+ * pairs in PHYSICAL order (streamed through pinned staging, so a 32 GiB shard
+ * needs no 32 GiB host buffer).  save writes the WORKING state (after forward
+ * the layout is the plan's final qubit map, recorded in the header); load
+ * installs a file in the identity layout as the circuit's INITIAL state, like
+ * set_state_from_host.  state_layout reports the current map (n ints). */
+const char* qdc_circuit_save_state(qdc_circuit* c, const char* path);
+const char* qdc_circuit_load_state(qdc_circuit* c, const char* path);
+const char* qdc_circuit_state_layout(const qdc_circuit* c, int* logical_to_physical);
 /* DEVICE pointer of the working state (for callers that own device plumbing). */
 const char* qdc_circuit_state_device_ptr(qdc_circuit* c, void** device_ptr);
 /* Run on a caller-provided cudaStream_t (default: the legacy default stream). */
@@ -104,7 +117,8 @@ const char* qdc_circuit_set_stream(qdc_circuit* c, void* cuda_stream);
 /* Tunables: "fuse" (0 = one pass per instruction, 1 = tiled multi-gate passes),
  * "profile" (1 = time every launch group with CUDA events), "tile_bits",
  * "low_bits", "max_tile_gates" (geometry of the tiled passes; 0 = default),
- * "peer" (sharded: 1 = peer-memory swap kernel, 0 = NCCL send/recv). */
+ * "peer" (sharded: 1 = peer-memory swap kernel, 0 = NCCL send/recv),
+ * "soa" (f32 tile kernels: 1 = pair-lane shared-memory layout, 0 = interleaved). */
 const char* qdc_circuit_set_option(qdc_circuit* c, const char* key, long value);
 /* Execution statistics of the last run/forward/backward call. */
 typedef struct {

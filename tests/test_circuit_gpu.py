@@ -279,16 +279,19 @@ def test_fused_brickwork_equals_per_gate_executor(pkg, dtype):
     n, depth = 22, 12
     var, cts = bench.brickwork_inputs(n, depth, dtype)
     out = {}
-    for fuse in (0, 1, 2):
+    # (fuse, soa): soa = 0 selects the interleaved-layout f32 tile kernels, the f32 default being the
+    # pair-lane kernels (tile_soa_kernels.cuh); the key 3 is fuse = 1 with soa = 0
+    for key, fuse, soa in ((0, 0, 1), (1, 1, 1), (2, 2, 1), (3, 1, 0)):
         c = Circuit(n, precision=prec(dtype))
         c.set_option("fuse", fuse)
+        c.set_option("soa", soa)
         bench.build_brickwork(c, n, depth)
         dens = c.forward([], var)
         grads = c.backward([x.conj() for x in cts], [], var)
-        out[fuse] = (dens, grads, c.last_stats()["hbm_passes"])
+        out[key] = (dens, grads, c.last_stats()["hbm_passes"])
     tol = TOL[np.dtype(dtype)] * 10
     gscale = max(np.abs(g).max() for g in out[0][1])
-    for fuse in (1, 2):
+    for fuse in (1, 2, 3):
         assert_close_list(out[fuse][0], out[0][0], tol)
         assert max(np.abs(a - b).max() for a, b in zip(out[fuse][1], out[0][1])) / gscale < tol
         assert out[fuse][2] < out[0][2] / 3, "fusion must cut the number of HBM sweeps"
