@@ -51,6 +51,9 @@ struct Stats {
   uint64_t kernel_launches = 0, hbm_passes = 0, algorithmic_bytes = 0;
 };
 
+struct DensGroup;
+struct TileDensParams;
+
 struct GateList {
   const cplx_t* flat;
   const uint32_t* lens;
@@ -208,6 +211,7 @@ class Circuit {
   cudaStream_t stream_ = 0;
   Stats stats_;
   int opt_fuse_ = 2;          // 0: one pass per instruction, 1: tiled multi-gate passes, 2: + register-blocked forward
+  int opt_batch_dens_ = 1;    // 1: densities / density seeds of one program point share tiled sweeps (tile_dens_kernels.cuh)
   int opt_soa_ = 1;           // f32 tile kernels: 1 pair-lane shared-memory layout (tile_soa_kernels.cuh), 0 interleaved
   int opt_tile_bits_ = 0;  // 0: default for the precision
   int opt_low_bits_ = 0;
@@ -756,6 +760,7 @@ class Circuit {
     QDC_TRY(ensure_results(nslots));
     build_plan(all_dens);
     QDC_TRY(reset_state());
+    if (nslots) QDC_CUDA(cudaMemsetAsync(d_res_, 0, nslots * 32 * sizeof(double), stream_));
     QDC_TRY(run_forward(gp, all_dens));
     cur_map_ = plan_.final_map;
     // single read-back of every density
@@ -818,7 +823,9 @@ class Circuit {
         if (kind_is_dens(k) && (all_dens || kind_is_diff_dens(k))) dslot[i] = s++;
       }
     }
-    for (const qdc::Step& st : plan_.steps) {
+    const std::vector<qdc::Step>& steps = plan_.steps;
+    for (size_t si = 0; si < steps.size(); si++) {
+      const qdc::Step& st = steps[si];
       switch (st.type) {
         case qdc::ST_GATE:
           QDC_TRY(fwd_gate_step(st, gp));
@@ -831,17 +838,36 @@ class Circuit {
           PROF(CAT_EXCHANGE, 0, exchange(state_, st.gbit, st.lpos));
           break;
         case qdc::ST_DENS: {
-          double* dst = d_res_ + (size_t)dslot[st.inst] * 32;
-          if (st.p1 < 0) {
-            PROF(CAT_DENSITY, 1, eng_dens_q1(stream_, ws_, state_, st.p2, n_loc_, dst));
-          } else {
-            PROF(CAT_DENSITY, 1, eng_dens_q2(stream_, ws_, state_, st.p2, st.p1, n_loc_, dst));
-          }
-          account(2, 1, 1);
+          size_t sj = si;  // the run of densities requested at this program point
+          while (sj + 1 < steps.size() && steps[sj + 1].type == qdc::ST_DENS) sj++;
+          QDC_TRY(run_dens_run(si, sj, dslot));
+          si = sj;
           break;
         }
       }
     }
+    return nullptr;
+  }
+
+  const char* dens_single(const qdc::Step& st, const std::vector<long>& dslot) {
+    double* dst = d_res_ + (size_t)dslot[st.inst] * 32;
+    if (st.p1 < 0) {
+      PROF(CAT_DENSITY, 1, eng_dens_q1(stream_, ws_, state_, st.p2, n_loc_, dst));
+    } else {
+      PROF(CAT_DENSITY, 1, eng_dens_q2(stream_, ws_, state_, st.p2, st.p1, n_loc_, dst));
+    }
+    account(2, 1, 1);
+    return nullptr;
+  }
+
+  const char* seed_single(const qdc::Step& st, const std::vector<const cplx_t*>& dp, bool live) {
+    if (st.p1 < 0) {
+      PROF(CAT_SEED, live ? 3 : 2, eng_seed_q1(stream_, ws_, state_, bwd_, dp[st.inst], st.p2, n_loc_, live));
+    } else {
+      PROF(CAT_SEED, live ? 3 : 2,
+           eng_seed_q2(stream_, ws_, state_, bwd_, dp[st.inst], st.p2, st.p1, n_loc_, live));
+    }
+    account(1, 1, live ? 3 : 2);
     return nullptr;
   }
 
@@ -968,17 +994,10 @@ class Circuit {
       const qdc::Step& st = plan_.steps[si];
       switch (st.type) {
         case qdc::ST_DENS: {
-          const int k = insts_[st.inst].kind;
-          if (!kind_is_diff_dens(k)) break;
-          if (st.p1 < 0) {
-            PROF(CAT_SEED, live ? 3 : 2,
-                 eng_seed_q1(stream_, ws_, state_, bwd_, dp[st.inst], st.p2, n_loc_, live));
-          } else {
-            PROF(CAT_SEED, live ? 3 : 2,
-                 eng_seed_q2(stream_, ws_, state_, bwd_, dp[st.inst], st.p2, st.p1, n_loc_, live));
-          }
-          account(1, 1, live ? 3 : 2);
-          live = true;
+          size_t sj = si;  // the run of densities at this program point (walking backwards)
+          while (sj > 0 && plan_.steps[sj - 1].type == qdc::ST_DENS) sj--;
+          QDC_TRY(run_seed_run(sj, si, dp, &live));
+          si = sj;
           break;
         }
         case qdc::ST_GATE:
@@ -1017,6 +1036,12 @@ class Circuit {
   const char* run_tile_backward_rb(const qdc::Step& t, const std::vector<const cplx_t*>& gp,
                                    const std::vector<long>& vslot);
   void release_tiles();
+  // batched densities / seeds (tile_dens_kernels.cuh)
+  const char* fill_dens_params(const DensGroup& g, TileDensParams* p, std::vector<int>* tpos);
+  const char* run_dens_group(const DensGroup& g, const std::vector<long>& dslot);
+  const char* run_seed_group(const DensGroup& g, const std::vector<const cplx_t*>& dp, bool live);
+  const char* run_dens_run(size_t first, size_t last, const std::vector<long>& dslot);
+  const char* run_seed_run(size_t first, size_t last, const std::vector<const cplx_t*>& dp, bool* live);
   std::vector<char> diag_hilo_;  // diagonal gradient of this instruction came back in (hi,lo) order
   double* tile_partials_ = nullptr;
   size_t tile_partials_cap_ = 0;

@@ -72,6 +72,11 @@ struct SchedOptions {
   int min_tile_gates = 2;  // a tile pass must hold at least this many gates to beat streaming
   int max_tile_gates = 24; // capacity of the backward tile kernel's parameter block
   int group_bits = 4;      // register-block width: gates of a pass are grouped by <= this many positions
+  // Remap victims are taken from physical positions >= swap_min_pos when any such qubit is less urgent
+  // than the global one: the exchanged halves then interleave in runs of 2^pos amplitudes, and the
+  // measured exchange rate over NVLink (profiles/r1_exchange_bench_2gpu.txt) is 695 GB/s per direction
+  // for pos >= 4 (128-byte runs) against 320-510 GB/s for pos 0..3.  0 = pure farthest-next-use choice.
+  int swap_min_pos = 4;
 };
 
 class Scheduler {
@@ -296,14 +301,26 @@ class Scheduler {
     std::vector<int> globals, locals;
     for (int q = 0; q < o_.n; q++) (local(q) ? locals : globals).push_back(q);
     std::sort(globals.begin(), globals.end(), [&](int a, int b) { return nu[a] < nu[b]; });  // most urgent first
+    const int min_pos = std::min(o_.swap_min_pos, std::max(0, o_.n_loc - 1));
     std::sort(locals.begin(), locals.end(), [&](int a, int b) {
+      const bool la = map_[a] < min_pos, lb = map_[b] < min_pos;
+      if (la != lb) return lb;                   // positions with short runs last (slow exchanges)
       if (nu[a] != nu[b]) return nu[a] > nu[b];  // least urgent first
       return map_[a] > map_[b];                  // prefer high positions (cheaper, contiguous halves)
     });
     bool any = false;
-    for (size_t k = 0; k < globals.size() && k < locals.size(); k++) {
-      const int G = globals[k], L = locals[k];
-      if (!(nu[G] < nu[L])) break;
+    std::vector<char> used(locals.size(), 0);
+    for (size_t k = 0; k < globals.size(); k++) {
+      const int G = globals[k];
+      int pick = -1;  // first unused local (in preference order) that is less urgent than G
+      for (size_t j = 0; j < locals.size(); j++)
+        if (!used[j] && nu[G] < nu[locals[j]]) {
+          pick = (int)j;
+          break;
+        }
+      if (pick < 0) break;
+      used[pick] = 1;
+      const int L = locals[pick];
       Step st;
       st.type = ST_SWAP;
       st.gbit = map_[G] - o_.n_loc;

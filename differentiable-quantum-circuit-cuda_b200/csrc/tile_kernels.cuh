@@ -272,6 +272,60 @@ __device__ __forceinline__ void tile_diag(vec_t* smv, int nvec, const GateMat& D
   }
 }
 
+// Diagonal gate on tile bits a > b through the quad geometry: the four vectors of an item are the four
+// settings of (bit a, bit b), so vector c takes entry d[c] -- compile-time indices, no per-amplitude
+// selection (the select-based tile_diag / tile_rev_diag above compile to divergent branches over the
+// constant bank: 300+ instructions per vector).  One amplitude per vector (f64) or b >= 1.
+template <int NT>
+__device__ __forceinline__ void tile_diag_quad(vec_t* smv, const GeoQ2HH& geo, int nitems, const GateMat& D) {
+  for (int i0 = 0; i0 < nitems; i0 += NT) {  // uniform trip count
+    const uint32_t base = geo.base32((uint32_t)(i0 + threadIdx.x));
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      VecU v;
+      v.v = smv[base + geo.off32(c)];
+#pragma unroll
+      for (int e = 0; e < QDC_VA; e++) {
+        const real_t x = v.r[2 * e] * D.re[c] - v.r[2 * e + 1] * D.im[c];
+        const real_t y = v.r[2 * e] * D.im[c] + v.r[2 * e + 1] * D.re[c];
+        v.r[2 * e] = x;
+        v.r[2 * e + 1] = y;
+      }
+      smv[base + geo.off32(c)] = v.v;
+    }
+  }
+}
+
+template <int NT>
+__device__ __forceinline__ void tile_rev_diag_quad(vec_t* smf, vec_t* smb, const GeoQ2HH& geo, int nitems,
+                                                   const TileGateB& G, real_t* acc) {
+  for (int i0 = 0; i0 < nitems; i0 += NT) {  // uniform trip count
+    const uint32_t base = geo.base32((uint32_t)(i0 + threadIdx.x));
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      VecU vf, vb;
+      vf.v = smf[base + geo.off32(c)];
+      vb.v = smb[base + geo.off32(c)];
+#pragma unroll
+      for (int e = 0; e < QDC_VA; e++) {
+        const real_t fx = vf.r[2 * e] * G.inv.re[c] - vf.r[2 * e + 1] * G.inv.im[c];
+        const real_t fy = vf.r[2 * e] * G.inv.im[c] + vf.r[2 * e + 1] * G.inv.re[c];
+        vf.r[2 * e] = fx;
+        vf.r[2 * e + 1] = fy;
+        const real_t bx = vb.r[2 * e], by = vb.r[2 * e + 1];
+        if (G.slot >= 0) {
+          acc[2 * c] += bx * fx - by * fy;
+          acc[2 * c + 1] += bx * fy + by * fx;
+        }
+        vb.r[2 * e] = bx * G.tr.re[c] - by * G.tr.im[c];
+        vb.r[2 * e + 1] = bx * G.tr.im[c] + by * G.tr.re[c];
+      }
+      smf[base + geo.off32(c)] = vf.v;
+      smb[base + geo.off32(c)] = vb.v;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(QDC_TILE_NT_F, 6)
     k_tile_fwd(cplx_t* __restrict__ state, const __grid_constant__ TileFwdParams p) {
   extern __shared__ __align__(16) unsigned char tile_smem[];
@@ -311,6 +365,11 @@ __global__ void __launch_bounds__(QDC_TILE_NT_F, 6)
           geo.pv = G.a - QDC_LV;
           tile_apply<QDC_TILE_NT_F>(smv, geo, nvec / 2, G);
         }
+      } else if (G.b >= QDC_LV) {
+        GeoQ2HH geo;
+        geo.lv = G.b - QDC_LV;
+        geo.hv = G.a - QDC_LV;
+        tile_diag_quad<QDC_TILE_NT_F>(smv, geo, nvec / 4, G.m);
       } else {
         tile_diag<QDC_TILE_NT_F>(smv, nvec, G.m, G.a, G.b);
       }
@@ -448,6 +507,11 @@ __global__ void __launch_bounds__(QDC_TILE_NT_B, 3)
           geo.pv = G.a - QDC_LV;
           tile_rev<QDC_TILE_NT_B>(smf, smb, geo, nvec / 2, G, acc);
         }
+      } else if (G.b >= QDC_LV) {
+        GeoQ2HH geo;
+        geo.lv = G.b - QDC_LV;
+        geo.hv = G.a - QDC_LV;
+        tile_rev_diag_quad<QDC_TILE_NT_B>(smf, smb, geo, nvec / 4, G, acc);
       } else {
         tile_rev_diag<QDC_TILE_NT_B>(smf, smb, nvec, G, acc);
       }
@@ -506,8 +570,18 @@ __global__ void __launch_bounds__(QDC_TILE_NT_B, 3)
 static int g_tile_debug = 0;
 static int g_tile_stagger = 0;  // option "stagger": percent of the default start skew per gate of the pass.
                                 // Off by default: measured no gain (28 q: 558.2 vs 558.2 ms/step at 0 / 100 %), i.e. no convoy.
+static inline const char* make_tile_geo_bits(std::vector<int> bits, int n_loc, int low_bits, TileGeo* geo,
+                                             std::vector<int>* tile_pos_of);
 static inline const char* make_tile_geo(const qdc::Plan& plan, const qdc::Step& t, int n_loc, int low_bits,
                                         TileGeo* geo, std::vector<int>* tile_pos_of) {
+  return make_tile_geo_bits(
+      std::vector<int>(plan.tile_bits.begin() + t.tb_first, plan.tile_bits.begin() + t.tb_first + t.tb_count),
+      n_loc, low_bits, geo, tile_pos_of);
+}
+
+// Geometry of a tile over the physical positions `bits` (padded with the lowest unused positions).
+static inline const char* make_tile_geo_bits(std::vector<int> bits, int n_loc, int low_bits, TileGeo* geo,
+                                             std::vector<int>* tile_pos_of) {
   geo->debug = g_tile_debug;
   geo->stagger_ns = 0;
   geo->resident = 1;
@@ -516,7 +590,6 @@ static inline const char* make_tile_geo(const qdc::Plan& plan, const qdc::Step& 
     QDC_TRY(qdc_device_info(&di));
     geo->nsm = di.sm_count;
   }
-  std::vector<int> bits(plan.tile_bits.begin() + t.tb_first, plan.tile_bits.begin() + t.tb_first + t.tb_count);
   // pad with the lowest unused positions so that T >= log2(threads * vector) and runs stay whole
   int T = (int)bits.size();
   const int min_T = QDC_LV + 8 + 2;  // every thread gets at least one 4-vector quad item
@@ -582,9 +655,10 @@ static inline const char* tile_matrix(const cplx_t* gate, int kind, int form, bo
     to_hilo(m, swap);
     split<16>(m, re, im);
   } else {
-    for (int j = 0; j < 4; j++) {
-      re[j] = gate[j].x;
-      im[j] = (form == FORM_CONJ_TR) ? -gate[j].y : gate[j].y;
+    for (int j = 0; j < 4; j++) {  // entries in (hi,lo) order: j = 2 bit_hi + bit_lo
+      const int src = swap ? (((j & 1) << 1) | (j >> 1)) : j;
+      re[j] = gate[src].x;
+      im[j] = (form == FORM_CONJ_TR) ? -gate[src].y : gate[src].y;
     }
   }
   gm_fill(*out, re, im);
@@ -614,8 +688,8 @@ inline const char* Circuit::run_tile_forward(const qdc::Step& t, const std::vect
       G.b = tpos[swap ? st.p2 : st.p1];
     } else {
       G.type = TG_DIAG;
-      G.a = tpos[st.p2];
-      G.b = tpos[st.p1];
+      G.a = tpos[swap ? st.p1 : st.p2];
+      G.b = tpos[swap ? st.p2 : st.p1];
     }
   }
   const size_t smem = sizeof(cplx_t) << p.geo.T;
@@ -650,12 +724,12 @@ inline const char* Circuit::run_tile_backward(const qdc::Step& t, const std::vec
       const bool swap = st.p1 >= 0 && st.p2 < st.p1;
       QDC_TRY(tile_matrix(gp[st.inst], kind, kind_is_nonu(kind) ? FORM_INV : FORM_CONJ_TR, swap, &G.m));
       G.type = kind_is_q1(kind) ? TG_Q1 : (kind_is_q2dense(kind) ? TG_Q2 : TG_DIAG);
-      if (G.type == TG_Q2) {
+      if (G.type != TG_Q1) {
         G.a = tpos[swap ? st.p1 : st.p2];
         G.b = tpos[swap ? st.p2 : st.p1];
       } else {
         G.a = tpos[st.p2];
-        G.b = st.p1 >= 0 ? tpos[st.p1] : -1;
+        G.b = -1;
       }
     }
     const size_t smem = sizeof(cplx_t) << p.geo.T;
@@ -687,13 +761,14 @@ inline const char* Circuit::run_tile_backward(const qdc::Step& t, const std::vec
     QDC_TRY(tile_matrix(gp[st.inst], kind, kind_is_nonu(kind) ? FORM_INV : FORM_CONJ_TR, swap, &G.inv));
     QDC_TRY(tile_matrix(gp[st.inst], kind, kind_is_diag(kind) ? FORM_PLAIN : FORM_TR, swap, &G.tr));
     G.type = kind_is_q1(kind) ? TG_Q1 : (kind_is_q2dense(kind) ? TG_Q2 : TG_DIAG);
-    if (G.type == TG_Q2) {
+    if (G.type != TG_Q1) {
       G.a = tpos[swap ? st.p1 : st.p2];
       G.b = tpos[swap ? st.p2 : st.p1];
     } else {
       G.a = tpos[st.p2];
-      G.b = st.p1 >= 0 ? tpos[st.p1] : -1;
+      G.b = -1;
     }
+    if (G.type == TG_DIAG) diag_hilo_[st.inst] = swap;  // the gradient comes back in (hi,lo) order
     G.slot = (int)vslot[st.inst];
     h_slots.s[k] = G.slot;
   }

@@ -210,26 +210,48 @@ __device__ __forceinline__ void tile_apply_mix(vec_t* smv, int hv, int nitems, c
   }
 }
 
-// per-lane diagonal entries of vector i: lane e is amplitude 2 i + e
-__device__ __forceinline__ void diag_lanes(const GateMat& D, int i, int a, int b, float2& dr, float2& di, int& j0, int& j1) {
-  const int amp = 2 * i;
-  j0 = 2 * ((amp >> a) & 1) + ((amp >> b) & 1);
-  j1 = 2 * (((amp + 1) >> a) & 1) + (((amp + 1) >> b) & 1);
-  dr = make_float2(gm_sel4_re(D, j0), gm_sel4_re(D, j1));
-  di = make_float2(gm_sel4_im(D, j0), gm_sel4_im(D, j1));
+// Diagonal gates, entries in (hi,lo) order d[2 bit_a + bit_b], a > b (host: tile_matrix).
+//  * b >= 1: the four vectors of a quad item are the four settings of (bit a, bit b): vector c takes
+//    the CTA-uniform entry d[c] for both lanes -- broadcast operands, compile-time indices.
+//  * b == 0: the lanes ARE bit b: the two vectors of a pair item over bit a take the lane pairs
+//    (d[2h], d[2h+1]).
+// (A per-amplitude selection of the entry compiles to divergent branches over the constant bank:
+// measured 0.44 ms per diagonal reverse step at 26 q against 0.11 ms for a dense one-qubit gate.)
+__device__ __forceinline__ V4 cmul_bc(const V4& v, const float dr, const float di) {
+  V4 o;
+  o.re = ffma2(bc2(-di), v.im, fmul2(bc2(dr), v.re));
+  o.im = ffma2(bc2(dr), v.im, fmul2(bc2(di), v.re));
+  return o;
+}
+__device__ __forceinline__ V4 cmul_pair(const V4& v, const float2 dr, const float2 di) {
+  V4 o;
+  o.re = ffma2(neg2(di), v.im, fmul2(dr, v.re));
+  o.im = ffma2(dr, v.im, fmul2(di, v.re));
+  return o;
 }
 
 template <int NT>
-__device__ __forceinline__ void tile_diag_soa(vec_t* smv, int nvec, const GateMat& D, int a, int b) {
-  for (int i0 = 0; i0 < nvec; i0 += NT) {
-    const int i = i0 + threadIdx.x;
-    float2 dr, di;
-    int j0, j1;
-    diag_lanes(D, i, a, b, dr, di, j0, j1);
-    V4 v = ld4(smv + i), o;
-    o.re = ffma2(neg2(v.im), di, fmul2(v.re, dr));
-    o.im = ffma2(v.im, dr, fmul2(v.re, di));
-    st4(smv + i, o);
+__device__ __forceinline__ void tile_diag_soa_hh(vec_t* smv, const GeoQ2HH& geo, int nitems, const GateMat& D) {
+  for (int i0 = 0; i0 < nitems; i0 += NT) {
+    const uint32_t base = geo.base32((uint32_t)(i0 + threadIdx.x));
+#pragma unroll
+    for (int c = 0; c < 4; c++) st4(smv + base + geo.off32(c), cmul_bc(ld4(smv + base + geo.off32(c)), D.re[c], D.im[c]));
+  }
+}
+
+template <int NT>
+__device__ __forceinline__ void tile_diag_soa_lh(vec_t* smv, int hv, int nitems, const GateMat& D) {
+  float2 dr[2], di[2];
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+    dr[h] = make_float2(D.re[2 * h], D.re[2 * h + 1]);
+    di[h] = make_float2(D.im[2 * h], D.im[2 * h + 1]);
+  }
+  for (int i0 = 0; i0 < nitems; i0 += NT) {
+    const uint32_t base = ins0_32((uint32_t)(i0 + threadIdx.x), hv);
+#pragma unroll
+    for (int h = 0; h < 2; h++)
+      st4(smv + base + ((uint32_t)h << hv), cmul_pair(ld4(smv + base + ((uint32_t)h << hv)), dr[h], di[h]));
   }
 }
 
@@ -266,8 +288,13 @@ __global__ void __launch_bounds__(QDC_TILE_NT_F, 6)
           geo.pv = G.a - QDC_LV;
           tile_apply_soa<QDC_TILE_NT_F>(smv, geo, nvec / 2, G.m);
         }
+      } else if (G.b == 0) {
+        tile_diag_soa_lh<QDC_TILE_NT_F>(smv, G.a - 1, nvec / 2, G.m);
       } else {
-        tile_diag_soa<QDC_TILE_NT_F>(smv, nvec, G.m, G.a, G.b);
+        GeoQ2HH geo;
+        geo.lv = G.b - QDC_LV;
+        geo.hv = G.a - QDC_LV;
+        tile_diag_soa_hh<QDC_TILE_NT_F>(smv, geo, nvec / 4, G.m);
       }
       __syncthreads();
     }
@@ -336,31 +363,64 @@ __device__ __forceinline__ void tile_rev_mix(vec_t* smf, vec_t* smb, int hv, int
 }
 
 template <int NT>
-__device__ __forceinline__ void tile_rev_diag_soa(vec_t* smf, vec_t* smb, int nvec, const TileGateB& G,
-                                                  real_t (&acc)[32]) {
-  for (int i0 = 0; i0 < nvec; i0 += NT) {
-    const int i = i0 + threadIdx.x;
-    float2 ir, ii, dr, di;
-    int j0, j1;
-    diag_lanes(G.inv, i, G.a, G.b, ir, ii, j0, j1);
-    diag_lanes(G.tr, i, G.a, G.b, dr, di, j0, j1);
-    const V4 f = ld4(smf + i), b = ld4(smb + i);
-    V4 fo, bo;
-    fo.re = ffma2(neg2(f.im), ii, fmul2(f.re, ir));
-    fo.im = ffma2(f.im, ir, fmul2(f.re, ii));
-    if (G.slot >= 0) {
-      const float2 pr = ffma2(neg2(b.im), fo.im, fmul2(b.re, fo.re));
-      const float2 pi = ffma2(b.im, fo.re, fmul2(b.re, fo.im));
+__device__ __forceinline__ void tile_rev_diag_soa_hh(vec_t* smf, vec_t* smb, const GeoQ2HH& geo, int nitems,
+                                                     const TileGateB& G, real_t (&acc)[32]) {
+  float2 are[4], aim[4];
 #pragma unroll
-      for (int jj = 0; jj < 4; jj++) {
-        acc[2 * jj] += ((j0 == jj) ? pr.x : 0.f) + ((j1 == jj) ? pr.y : 0.f);
-        acc[2 * jj + 1] += ((j0 == jj) ? pi.x : 0.f) + ((j1 == jj) ? pi.y : 0.f);
+  for (int c = 0; c < 4; c++) are[c] = aim[c] = make_float2(0.f, 0.f);
+  for (int i0 = 0; i0 < nitems; i0 += NT) {
+    const uint32_t base = geo.base32((uint32_t)(i0 + threadIdx.x));
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      const V4 f = cmul_bc(ld4(smf + base + geo.off32(c)), G.inv.re[c], G.inv.im[c]);
+      const V4 b = ld4(smb + base + geo.off32(c));
+      if (G.slot >= 0) {
+        are[c] = ffma2(neg2(b.im), f.im, ffma2(b.re, f.re, are[c]));
+        aim[c] = ffma2(b.im, f.re, ffma2(b.re, f.im, aim[c]));
       }
+      st4(smf + base + geo.off32(c), f);
+      st4(smb + base + geo.off32(c), cmul_bc(b, G.tr.re[c], G.tr.im[c]));
     }
-    bo.re = ffma2(neg2(b.im), di, fmul2(b.re, dr));
-    bo.im = ffma2(b.im, dr, fmul2(b.re, di));
-    st4(smf + i, fo);
-    st4(smb + i, bo);
+  }
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    acc[2 * c] = are[c].x + are[c].y;
+    acc[2 * c + 1] = aim[c].x + aim[c].y;
+  }
+}
+
+template <int NT>
+__device__ __forceinline__ void tile_rev_diag_soa_lh(vec_t* smf, vec_t* smb, int hv, int nitems, const TileGateB& G,
+                                                     real_t (&acc)[32]) {
+  float2 ir[2], ii[2], dr[2], di[2], are[2], aim[2];
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+    ir[h] = make_float2(G.inv.re[2 * h], G.inv.re[2 * h + 1]);
+    ii[h] = make_float2(G.inv.im[2 * h], G.inv.im[2 * h + 1]);
+    dr[h] = make_float2(G.tr.re[2 * h], G.tr.re[2 * h + 1]);
+    di[h] = make_float2(G.tr.im[2 * h], G.tr.im[2 * h + 1]);
+    are[h] = aim[h] = make_float2(0.f, 0.f);
+  }
+  for (int i0 = 0; i0 < nitems; i0 += NT) {
+    const uint32_t base = ins0_32((uint32_t)(i0 + threadIdx.x), hv);
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const V4 f = cmul_pair(ld4(smf + base + ((uint32_t)h << hv)), ir[h], ii[h]);
+      const V4 b = ld4(smb + base + ((uint32_t)h << hv));
+      if (G.slot >= 0) {
+        are[h] = ffma2(neg2(b.im), f.im, ffma2(b.re, f.re, are[h]));
+        aim[h] = ffma2(b.im, f.re, ffma2(b.re, f.im, aim[h]));
+      }
+      st4(smf + base + ((uint32_t)h << hv), f);
+      st4(smb + base + ((uint32_t)h << hv), cmul_pair(b, dr[h], di[h]));
+    }
+  }
+#pragma unroll
+  for (int h = 0; h < 2; h++) {  // lane e of pair h is the entry j = 2 h + e: no lane fold
+    acc[2 * (2 * h)] = are[h].x;
+    acc[2 * (2 * h) + 1] = aim[h].x;
+    acc[2 * (2 * h + 1)] = are[h].y;
+    acc[2 * (2 * h + 1) + 1] = aim[h].y;
   }
 }
 
@@ -415,8 +475,13 @@ __global__ void __launch_bounds__(QDC_TILE_NT_B, 3)
           geo.pv = G.a - QDC_LV;
           tile_rev_soa<QDC_TILE_NT_B>(smf, smb, geo, nvec / 2, G, acc);
         }
+      } else if (G.b == 0) {
+        tile_rev_diag_soa_lh<QDC_TILE_NT_B>(smf, smb, G.a - 1, nvec / 2, G, acc);
       } else {
-        tile_rev_diag_soa<QDC_TILE_NT_B>(smf, smb, nvec, G, acc);
+        GeoQ2HH geo;
+        geo.lv = G.b - QDC_LV;
+        geo.hv = G.a - QDC_LV;
+        tile_rev_diag_soa_hh<QDC_TILE_NT_B>(smf, smb, geo, nvec / 4, G, acc);
       }
       real_t* part = sm_part + (size_t)(g & 1) * NW * 32;
 #ifdef QDC_EXPERIMENT_NO_FLUSH  // timing experiment only (gradients wrong): cost of the per-gate reduction

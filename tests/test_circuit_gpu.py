@@ -295,3 +295,59 @@ def test_fused_brickwork_equals_per_gate_executor(pkg, dtype):
         assert_close_list(out[fuse][0], out[0][0], tol)
         assert max(np.abs(a - b).max() for a, b in zip(out[fuse][1], out[0][1])) / gscale < tol
         assert out[fuse][2] < out[0][2] / 3, "fusion must cut the number of HBM sweeps"
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_batched_densities_and_seeds_match_oracle_and_per_density_sweeps(pkg, dtype):
+    """all densities / seeds of one program point in shared tiled sweeps
+    (tile_dens_kernels.cuh).  A program point with more densities than one tile holds (q1 and q2,
+    both qubit orders, on bit 0, differentiable mixed with plain) between two gate layers."""
+    from quantum_differentiable_circuit import Circuit
+    n = 14
+    rng = np.random.default_rng(11)
+
+    def build(c):
+        for i in range(0, n - 1, 2):
+            c.add_q2_var_gate(i + 1, i)
+        for i in range(n - 1):                     # 13 q2 densities, alternating qubit order
+            (c.get_q2_dens_op_with_grad if i % 3 else c.get_q2_dens_op)(*((i, i + 1) if i % 2 else (i + 1, i)))
+        for i in range(0, n, 3):                   # q1 densities incl. bit 0
+            c.get_q1_dens_op_with_grad(i)
+        c.get_q2_dens_op_with_grad(n - 1, 0)       # a far pair
+        for i in range(1, n - 1, 2):
+            c.add_q2_var_gate(i, i + 1)
+        c.add_q1_var_gate(0)
+        for i in range(0, n - 1, 2):               # a second program point
+            c.get_q2_dens_op_with_grad(i, i + 1)
+
+    o = OracleCircuit(n)
+    build(o)
+    var = []
+    for kind, *_ in o.instructions:
+        if kind == 1:
+            var.append(haar_unitary(rng, 4, dtype).reshape(-1))
+        elif kind == 8:
+            var.append(haar_unitary(rng, 2, dtype).reshape(-1))
+    dens_o = o.forward([], var)
+    cts = []
+    for d in dens_o:
+        a = rng.normal(size=d.shape) + 1j * rng.normal(size=d.shape)
+        cts.append(((a + a.conj().T) / 2).astype(dtype))
+    grads_o = vjp(o, var, [], cts)
+    run_o = o.run([], var)
+    tol = TOL[np.dtype(dtype)] * 10
+    gscale = max(np.abs(g).max() for g in grads_o)
+    launches = {}
+    for batch in (1, 0):
+        c = Circuit(n, precision=prec(dtype))
+        c.set_option("tile_bits", 11)
+        c.set_option("batch_dens", batch)
+        build(c)
+        assert_close_list(c.run([], var), run_o, tol)
+        dens = c.forward([], var)
+        launches[batch] = c.last_stats()["hbm_passes"]
+        assert_close_list(dens, dens_o, tol)
+        grads = c.backward([ct.conj() for ct in cts], [], var)
+        launches[batch] += c.last_stats()["hbm_passes"]
+        assert max(np.abs(a - b).max() for a, b in zip(grads, grads_o)) / gscale < tol
+    assert launches[1] < launches[0] - 20, launches
