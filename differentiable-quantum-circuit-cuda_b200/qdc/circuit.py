@@ -66,28 +66,70 @@ class _AutodiffRun:
         return self.forward(var_gates, const_gates)
 
 
+def _torch_gather(tensors, np_dtype):
+    """All gate tensors -> NumPy with ONE device-to-host transfer (the
+    reference converts gate by gate, src/qdc/circuit.py:173-195, i.e. one blocking copy per gate
+    when the parameters live on the GPU)."""
+    import torch
+    if not tensors:
+        return []
+    tdt = torch.complex64 if np_dtype == np.complex64 else torch.complex128
+    flat = torch.cat([t.detach().reshape(-1).to(tdt) for t in tensors])
+    host = flat.cpu().numpy()
+    out, o = [], 0
+    for t in tensors:
+        out.append(host[o:o + t.numel()].reshape(tuple(t.shape)))
+        o += t.numel()
+    return out
+
+
+def _torch_scatter(arrays, like):
+    """NumPy results -> tensors on the device / dtype of `like` with ONE host-to-device transfer."""
+    import torch
+    if not arrays:
+        return []
+    flat = torch.from_numpy(np.concatenate([np.ascontiguousarray(a).reshape(-1) for a in arrays]))
+    flat = flat.to(device=like[0].device)
+    out, o = [], 0
+    for a, t in zip(arrays, like):
+        out.append(flat[o:o + a.size].reshape(tuple(t.shape)).to(t.dtype))
+        o += a.size
+    return out
+
+
 def _torch_apply(run: _AutodiffRun, var_gates, const_gates):
     import torch
 
     n_var = len(var_gates)
+    as_t = lambda g: g if isinstance(g, torch.Tensor) else torch.as_tensor(np.asarray(g))  # noqa: E731
+    var_gates, const_gates = [as_t(g) for g in var_gates], [as_t(g) for g in const_gates]
+    dt = run._c.dtype
+    dev = next((g.device for g in var_gates + const_gates if g.is_cuda), torch.device("cpu"))
 
     class _Fn(torch.autograd.Function):
         @staticmethod
         def forward(ctx, *gates):
-            vg, cg = gates[:n_var], gates[n_var:]
-            ctx.save_for_backward(*gates)
-            dens = run.forward(vg, cg)
-            return tuple(torch.from_numpy(d) for d in dens)
+            host = _torch_gather(list(gates), dt)     # one D2H for every gate of the circuit
+            ctx.host_gates = host
+            dens = run._c.forward(host[n_var:], host[:n_var])
+            flat = torch.from_numpy(np.concatenate([d.reshape(-1) for d in dens]) if dens else np.zeros(0, dt))
+            flat = flat.to(dev)                       # one H2D for every density
+            out, o = [], 0
+            for d in dens:
+                out.append(flat[o:o + d.size].reshape(d.shape))
+                o += d.size
+            ctx.var_like = gates[:n_var]
+            return tuple(out)
 
         @staticmethod
         def backward(ctx, *grad_outputs):
-            gates = ctx.saved_tensors
-            vg, cg = gates[:n_var], gates[n_var:]
-            # torch's complex gradient is the conjugate of the JAX cotangent
-            cts = [g.detach().cpu().numpy().conj() for g in grad_outputs]
-            grads = run.vjp(vg, cg, cts)
-            out = [torch.from_numpy(g.conj()).to(v.dtype).reshape(v.shape) for g, v in zip(grads, vg)]
-            return tuple(out) + (None,) * len(cg)
+            host = ctx.host_gates
+            # torch's complex gradient is the conjugate of the JAX cotangent; Circuit.backward wants the
+            # conjugated JAX cotangent (src/qdc/circuit.py:193), i.e. torch's gradient as it is
+            cts = _torch_gather(list(grad_outputs), dt)
+            grads = run._c.backward(cts, host[n_var:], host[:n_var])
+            out = _torch_scatter([g.conj() for g in grads], ctx.var_like)
+            return tuple(out) + (None,) * (len(host) - n_var)
 
     return list(_Fn.apply(*var_gates, *const_gates))
 
