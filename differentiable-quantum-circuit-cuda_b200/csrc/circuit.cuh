@@ -831,7 +831,7 @@ class Circuit {
           QDC_TRY(fwd_gate_step(st, gp));
           break;
         case qdc::ST_TILE:
-          if (opt_fuse_ >= 2) QDC_TRY(run_tile_forward_rb(st, gp, false));
+          if (opt_fuse_ >= 2) QDC_TRY(run_tile_forward_blocked(st, gp, false));
           else QDC_TRY(run_tile_forward(st, gp));
           break;
         case qdc::ST_SWAP:
@@ -1013,7 +1013,7 @@ class Circuit {
             else
 #endif
             if (live) QDC_TRY(run_tile_backward(st, gp, vslot, live));
-            else QDC_TRY(run_tile_forward_rb(st, gp, true));
+            else QDC_TRY(run_tile_forward_blocked(st, gp, true));
           } else {
             QDC_TRY(run_tile_backward(st, gp, vslot, live));
           }
@@ -1035,6 +1035,14 @@ class Circuit {
   const char* run_tile_forward_rb(const qdc::Step& t, const std::vector<const cplx_t*>& gp, bool uncompute);
   const char* run_tile_backward_rb(const qdc::Step& t, const std::vector<const cplx_t*>& gp,
                                    const std::vector<long>& vslot);
+  const char* run_tile_forward_rbs(const qdc::Step& t, const std::vector<const cplx_t*>& gp, bool uncompute);
+  // register-blocked forward / un-compute pass: pair-lane kernel on f32 (tile_rb_soa_kernels.cuh)
+  const char* run_tile_forward_blocked(const qdc::Step& t, const std::vector<const cplx_t*>& gp, bool uncompute) {
+#ifndef QDC_F64
+    if (opt_soa_) return run_tile_forward_rbs(t, gp, uncompute);
+#endif
+    return run_tile_forward_rb(t, gp, uncompute);
+  }
   void release_tiles();
   // batched densities / seeds (tile_dens_kernels.cuh)
   const char* fill_dens_params(const DensGroup& g, TileDensParams* p, std::vector<int>* tpos);

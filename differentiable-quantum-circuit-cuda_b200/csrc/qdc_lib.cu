@@ -5,6 +5,7 @@
 #include "primitives_abi.cuh"
 #include "tile_rb_kernels.cuh"
 #include "tile_soa_kernels.cuh"
+#include "tile_rb_soa_kernels.cuh"
 #include "tile_dens_kernels.cuh"
 
 struct qdc_circuit {
