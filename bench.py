@@ -323,6 +323,22 @@ def run_ours(args):
                     "avg_launch_ms": round(e["ms"] / e["launches"], 4),
                     "algorithmic_bytes_per_launch": e["algorithmic_bytes"] // e["launches"],
                     "share_of_step": round(e["ms"] / dev_ms, 4)}
+    # DRAM traffic of one launch of the dominant kernel: the ncu capture under profiles/ (one reverse pass
+    # reads + writes state and adjoint once = 4*S whatever the number of fused gates), scaled by the shard size
+    if roofline and roofline["kernel"] == "tile_bwd":
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+            if tr["precision"] == args.precision:
+                scale = 2.0 ** (args.qubits - tr["qubits"])
+                roofline["traffic"] = int((tr["dram_bytes_read"] + tr["dram_bytes_write"]) * scale)
+                roofline["traffic_source"] = ("ncu dram__bytes_read+write of one k_tile_bwd_soa launch at %d q "
+                                              "(profiles/r1_traffic_32q_bwd.csv)" % tr["qubits"]) + \
+                                             ("" if scale == 1.0 else ", scaled by the shard size")
+                roofline["traffic_note"] = ("a launch applies %.1f gates on average: algorithmic bytes = 4*S per "
+                                            "gate, DRAM traffic = 4*S per launch (no re-reads)"
+                                            % (roofline["algorithmic_bytes_per_launch"] / (4.0 * (int(np.dtype(dtype).itemsize) << args.qubits))))
+        except Exception:  # noqa: BLE001
+            pass
     total_alg = sum(e["algorithmic_bytes"] for e in prof.values())
     # Work unit = one gate applied to one 2^local_qubits-amplitude shard.  A sharded run applies every
     # gate to `world` shards, so the whole-job aggregate is world * gates / time (weak scaling: per-GPU
@@ -341,7 +357,8 @@ def run_ours(args):
                    "l2": "inputs (state + adjoint) far larger than L2; no flush needed",
                    "exchange": (("peer-memory swap kernel (NVLink, CUDA IPC)" if circ.peer_exchange else
                                  "NCCL send/recv + pack/unpack") if world > 1 else None),
-                   "executor": ["one pass per gate", "tiled multi-gate passes", "register-blocked tiled passes"][args.fuse]},
+                   "executor": ["one pass per gate", "tiled multi-gate passes", "register-blocked tiled passes"][args.fuse]
+                               + (", pair-lane smem layout" if args.precision == "f32" and args.soa and args.fuse else "")},
         "effective_hbm_gbs": round(total_alg * world / (dev_ms * 1e-3) / 1e9, 1),
         "effective_hbm_frac": round(total_alg / (dev_ms * 1e-3) / 1e9 / peak, 4),
         "roofline": roofline,
