@@ -387,3 +387,30 @@ def test_batched_densities_and_seeds_match_oracle_and_per_density_sweeps(pkg, dt
         launches[batch] += c.last_stats()["hbm_passes"]
         assert max(np.abs(a - b).max() for a, b in zip(grads, grads_o)) / gscale < tol
     assert launches[1] < launches[0] - 20, launches
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_vqse_default_tile_geometry_equals_per_gate_executor(pkg, dtype):
+    """The VQSE ansatz (diagonal ZZ ring + X rotations, ring densities incl. the far pair (0, n-1)) at n = 21
+    with the DEFAULT tile geometry (2^12 / 2^11 tiles): select-free diagonal paths, one-qubit gates, lane-mixing
+    gates on qubit 0, batched densities / seeds -- against the per-instruction executor."""
+    from quantum_differentiable_circuit import Circuit
+    n, layers = 21, 2
+    rng = np.random.default_rng(7)
+    gates = vqse_gates(rng.normal(size=2 * layers), n, dtype)
+    h = tfim_h(dtype)
+    init = (np.ones(1 << n) / np.sqrt(1 << n)).astype(dtype)
+    out = {}
+    for fuse in (0, 1, 2):
+        c = Circuit(n, precision=prec(dtype))
+        c.set_option("fuse", fuse)
+        c.set_state_from_vector(init)
+        build_vqse(c, n, layers)
+        dens = c.forward([], gates)
+        grads = c.backward([h.T.copy().conj() for _ in dens], [], gates)
+        out[fuse] = (dens, grads)
+    tol = TOL[np.dtype(dtype)] * 10
+    gscale = max(np.abs(g).max() for g in out[0][1])
+    for fuse in (1, 2):
+        assert_close_list(out[fuse][0], out[0][0], tol)
+        assert max(np.abs(a - b).max() for a, b in zip(out[fuse][1], out[0][1])) / gscale < tol
