@@ -632,9 +632,22 @@ inline void Circuit::release_tiles() {
 static inline const char* tile_grid(const void* kernel, int threads, size_t smem, uint64_t ntiles, int* grid) {
   DeviceInfo di;
   QDC_TRY(qdc_device_info(&di));
-  QDC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int bps = 0;
-  QDC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kernel, threads, smem));
+  // resident CTAs per SM of (kernel, threads, smem) on this device: queried once (the attribute call and the
+  // occupancy query cost more than the launch itself on small registers)
+  struct Entry { const void* kernel; int threads, device; size_t smem; int bps; };
+  static thread_local std::vector<Entry> cache;
+  int bps = -1;
+  for (const Entry& e : cache)
+    if (e.kernel == kernel && e.threads == threads && e.smem == smem && e.device == di.device) bps = e.bps;
+  if (bps < 0) {
+    size_t allowed = 0;  // the attribute is a per-kernel MAXIMUM: only ever raise it
+    for (const Entry& e : cache)
+      if (e.kernel == kernel && e.device == di.device && e.smem > allowed) allowed = e.smem;
+    if (smem > allowed)
+      QDC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    QDC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kernel, threads, smem));
+    cache.push_back(Entry{kernel, threads, di.device, smem, bps});
+  }
   if (bps < 1) return qdc_errf("tile kernel does not fit on an SM (%zu bytes of shared memory).", smem);
   const uint64_t cap = (uint64_t)di.sm_count * bps;
   *grid = (int)(ntiles < cap ? ntiles : cap);
