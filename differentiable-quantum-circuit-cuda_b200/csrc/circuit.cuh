@@ -211,11 +211,16 @@ class Circuit {
   cudaStream_t stream_ = 0;
   Stats stats_;
   int opt_fuse_ = 2;          // 0: one pass per instruction, 1: tiled multi-gate passes, 2: + register-blocked forward
+  int opt_tile_strategy_ = 1;  // scheduler.hpp: 1 window growth, 0 first-fit tiling
   int opt_batch_dens_ = 1;    // 1: densities / density seeds of one program point share tiled sweeps (tile_dens_kernels.cuh)
   int opt_soa_ = 1;           // f32 tile kernels: 1 pair-lane shared-memory layout (tile_soa_kernels.cuh), 0 interleaved
   int opt_tile_bits_ = 0;  // 0: default for the precision
   int opt_low_bits_ = 0;
-  int opt_max_tile_gates_ = 24;
+#ifdef QDC_F64
+  int opt_max_tile_gates_ = 24;  // = QDC_TILE_MAXG_B, the capacity of the reverse kernel's parameter block
+#else
+  int opt_max_tile_gates_ = 32;
+#endif
   Profiler prof_;
   qdc::Plan plan_;            // plan of the last forward sweep (backward replays it reversed)
   bool plan_all_dens_ = false;
@@ -582,6 +587,7 @@ class Circuit {
       so.tile_bits = opt_tile_bits_ ? opt_tile_bits_ : default_tile_bits();
       so.low_bits = opt_low_bits_ ? opt_low_bits_ : default_low_bits();
       so.max_tile_gates = opt_max_tile_gates_;
+      so.tile_strategy = opt_tile_strategy_;
       if (so.tile_bits > n_loc_) so.tile_bits = n_loc_;
       if (so.tile_bits < min_tile_bits() || so.low_bits > so.tile_bits - 2) so.tile_bits = 0;  // too small to tile
     }
@@ -595,7 +601,7 @@ class Circuit {
   void build_plan(bool all_dens) {
     const qdc::SchedOptions so = sched_options();
     const std::vector<long> key = {(long)insts_.size(), all_dens ? 1L : 0L, so.n, so.n_loc, so.tile_bits, so.low_bits,
-                                   so.max_tile_gates, so.min_tile_gates, so.group_bits, so.swap_min_pos};
+                                   so.max_tile_gates, so.min_tile_gates, so.group_bits, so.swap_min_pos, so.tile_strategy};
     if (key == plan_key_ && !plan_.steps.empty()) return;
     plan_key_ = key;
     std::vector<qdc::SchedInst> si(insts_.size());
