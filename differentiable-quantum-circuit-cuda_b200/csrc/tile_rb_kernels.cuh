@@ -21,7 +21,7 @@
 #endif
 #define QDC_RB 4            // positions per register block
 #define QDC_RB_AMPS 16
-#define QDC_RB_MAXGRP 24
+#define QDC_RB_MAXGRP 32  // >= the largest number of gates in a pass (every gate its own group in the worst case)
 
 struct RbGroup {
   BitDeposit map;         // block index (T-4 bits) -> tile-local element index of the block's element 0
