@@ -241,6 +241,10 @@ def run_ours(args):
         circ.set_option("peer", args.peer)
     if args.precision == "f32":
         circ.set_option("soa", args.soa)
+    if args.rb_policy >= 0:
+        circ.set_option("rb_policy", args.rb_policy)
+    if args.batch_dens >= 0:
+        circ.set_option("batch_dens", args.batch_dens)
     if args.tile_strategy >= 0:
         circ.set_option("tile_strategy", args.tile_strategy)
     if args.stagger >= 0:
@@ -448,6 +452,8 @@ def main():
     ap.add_argument("--max-tile-gates", type=int, default=0)
     ap.add_argument("--peer", type=int, default=1, help="sharded: 1 peer-memory swap kernel, 0 NCCL send/recv")
     ap.add_argument("--soa", type=int, default=1, help="f32 tile kernels: 1 pair-lane smem layout, 0 interleaved layout")
+    ap.add_argument("--rb-policy", type=int, default=-1, help="fuse=2 forward: 0 never register-block, 1 always, 2 by gate mix (default)")
+    ap.add_argument("--batch-dens", type=int, default=-1, help="0: one sweep per density / seed")
     ap.add_argument("--tile-strategy", type=int, default=-1, help="scheduler tiling: 1 window growth (default), 0 first-fit")
     ap.add_argument("--stagger", type=int, default=-1, help="CTA start skew, percent of the library default (0: off)")
     ap.add_argument("--tile-debug", type=int, default=0, help="profiling aid (1: no HBM traffic, 2: no gates); invalid results")

@@ -1051,12 +1051,28 @@ class Circuit {
   const char* run_tile_backward_rb(const qdc::Step& t, const std::vector<const cplx_t*>& gp,
                                    const std::vector<long>& vslot);
   const char* run_tile_forward_rbs(const qdc::Step& t, const std::vector<const cplx_t*>& gp, bool uncompute);
-  // register-blocked forward / un-compute pass: pair-lane kernel on f32 (tile_rb_soa_kernels.cuh)
+  // Forward / un-compute pass of the default executor (fuse = 2).  Register blocking pays when a block's
+  // gates are cheap relative to a shared-memory round trip of the tile (one-qubit and diagonal gates: VQSE-28
+  // forward 347 vs 480 ms); for passes dominated by dense two-qubit gates the one-gate-per-sweep pair-lane
+  // kernel is faster (28 q brickwork forward 234 vs 264 ms: the blocked kernel's strided block accesses cost
+  // it 57 % of its shared wavefronts in bank conflicts, profiles/r1_tile_fwd_rbs_28q_ncu.txt).
+  int opt_rb_policy_ = 2;  // 0: never register-block, 1: always, 2: by gate mix (default)
   const char* run_tile_forward_blocked(const qdc::Step& t, const std::vector<const cplx_t*>& gp, bool uncompute) {
+    bool blocked = opt_rb_policy_ == 1;
+    if (opt_rb_policy_ == 2) {
+      int dense_q2 = 0;
+      for (int k = 0; k < t.count; k++)
+        dense_q2 += kind_is_q2dense(insts_[plan_.tile_steps[t.first + k].inst].kind) ? 1 : 0;
+      blocked = 2 * dense_q2 <= t.count;
+    }
 #ifndef QDC_F64
-    if (opt_soa_) return run_tile_forward_rbs(t, gp, uncompute);
+    if (opt_soa_) {
+      if (blocked) return run_tile_forward_rbs(t, gp, uncompute);
+      return uncompute ? run_tile_backward(t, gp, std::vector<long>(), false) : run_tile_forward(t, gp);
+    }
 #endif
-    return run_tile_forward_rb(t, gp, uncompute);
+    if (blocked) return run_tile_forward_rb(t, gp, uncompute);
+    return uncompute ? run_tile_backward(t, gp, std::vector<long>(), false) : run_tile_forward(t, gp);
   }
   void release_tiles();
   // batched densities / seeds (tile_dens_kernels.cuh)

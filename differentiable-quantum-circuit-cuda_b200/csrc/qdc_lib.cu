@@ -132,6 +132,7 @@ QDC_EXPORT const char* qdc_circuit_set_option(qdc_circuit* c, const char* key, l
   else if (strcmp(key, "profile") == 0) c->impl.prof_.on = value != 0;
   else if (strcmp(key, "tile_bits") == 0) c->impl.opt_tile_bits_ = (int)value;
   else if (strcmp(key, "low_bits") == 0) c->impl.opt_low_bits_ = (int)value;
+  else if (strcmp(key, "rb_policy") == 0) c->impl.opt_rb_policy_ = (int)value;  // fuse=2 forward: 0 never / 1 always / 2 by gate mix
   else if (strcmp(key, "tile_strategy") == 0) c->impl.opt_tile_strategy_ = (int)value;  // 1 window growth, 0 first-fit
   else if (strcmp(key, "batch_dens") == 0) c->impl.opt_batch_dens_ = (int)value;  // 0: one sweep per density / seed
   else if (strcmp(key, "soa") == 0) c->impl.opt_soa_ = (int)value;    // f32 tile kernels: 0 selects the interleaved-layout kernels

@@ -592,7 +592,10 @@ static inline const char* make_tile_geo_bits(std::vector<int> bits, int n_loc, i
   }
   // pad with the lowest unused positions so that T >= log2(threads * vector) and runs stay whole
   int T = (int)bits.size();
-  const int min_T = QDC_LV + 8 + 2;  // every thread gets at least one 4-vector quad item
+  // every thread gets at least one 4-vector quad item (QDC_LV + 10), and the register-blocked kernels need one
+  // 2^4-amplitude block per thread of a 128-thread CTA (11): a 2^10 f64 tile made their upper 64 threads redo
+  // the blocks of the lower 64 (found with window-grown tiles that close before the bit budget is used up)
+  const int min_T = (QDC_LV + 8 + 2) > 11 ? (QDC_LV + 8 + 2) : 11;
   for (int p = 0; T < min_T && p < n_loc; p++) {
     if (std::find(bits.begin(), bits.end(), p) == bits.end()) {
       bits.push_back(p);

@@ -317,20 +317,28 @@ def test_fused_brickwork_equals_per_gate_executor(pkg, dtype):
     out = {}
     # (fuse, soa): soa = 0 selects the interleaved-layout f32 tile kernels, the f32 default being the
     # pair-lane kernels (tile_soa_kernels.cuh); the key 3 is fuse = 1 with soa = 0
-    for key, fuse, soa in ((0, 0, 1), (1, 1, 1), (2, 2, 1), (3, 1, 0)):
+    # keys 4-6: register-blocked forward forced on (rb_policy 1; the default picks it by gate mix) with the
+    # window-grown and the first-fit tiling, and with tiny passes (tiles that do not use up their bit budget)
+    variants = ((0, 0, 1, {}), (1, 1, 1, {}), (2, 2, 1, {}), (3, 1, 0, {}),
+                (4, 2, 1, {"rb_policy": 1}), (5, 2, 0, {"rb_policy": 1, "tile_strategy": 0}),
+                (6, 2, 1, {"rb_policy": 1, "max_tile_gates": 2}))
+    for key, fuse, soa, extra in variants:
         c = Circuit(n, precision=prec(dtype))
         c.set_option("fuse", fuse)
         c.set_option("soa", soa)
+        for k, v in extra.items():
+            c.set_option(k, v)
         bench.build_brickwork(c, n, depth)
         dens = c.forward([], var)
         grads = c.backward([x.conj() for x in cts], [], var)
         out[key] = (dens, grads, c.last_stats()["hbm_passes"])
     tol = TOL[np.dtype(dtype)] * 10
     gscale = max(np.abs(g).max() for g in out[0][1])
-    for fuse in (1, 2, 3):
+    for fuse in (1, 2, 3, 4, 5, 6):
         assert_close_list(out[fuse][0], out[0][0], tol)
         assert max(np.abs(a - b).max() for a, b in zip(out[fuse][1], out[0][1])) / gscale < tol
-        assert out[fuse][2] < out[0][2] / 3, "fusion must cut the number of HBM sweeps"
+        if fuse != 6:
+            assert out[fuse][2] < out[0][2] / 3, "fusion must cut the number of HBM sweeps"
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
