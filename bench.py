@@ -363,7 +363,8 @@ def run_ours(args):
                    "l2": "inputs (state + adjoint) far larger than L2; no flush needed",
                    "exchange": (("peer-memory swap kernel (NVLink, CUDA IPC)" if circ.peer_exchange else
                                  "NCCL send/recv + pack/unpack") if world > 1 else None),
-                   "executor": ["one pass per gate", "tiled multi-gate passes", "register-blocked tiled passes"][args.fuse]
+                   "executor": ["one pass per gate", "tiled multi-gate passes",
+                                "tiled multi-gate passes, forward kernel (register-blocked or per gate) by gate mix"][args.fuse]
                                + (", pair-lane smem layout" if args.precision == "f32" and args.soa and args.fuse else "")},
         "effective_hbm_gbs": round(total_alg * world / (dev_ms * 1e-3) / 1e9, 1),
         "effective_hbm_frac": round(total_alg / (dev_ms * 1e-3) / 1e9 / peak, 4),
