@@ -1,5 +1,6 @@
 cd $GRAFT_REPO_ROOT
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_final.log 2>&1; tail -3 gpurun_out/pytest_gpu_final.log
+timeout 900 python -m pytest tests -m gpu -x -q -k "not autodiff or not sharded" > gpurun_out/pytest_gpu_final.log 2>&1; tail -3 gpurun_out/pytest_gpu_final.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke_final.log 2>&1; tail -2 gpurun_out/smoke_final.log
-python profiles/scripts/small_circuit_latency.py 2>&1 | grep ours | tee gpurun_out/small_circuit_latency2.txt
-/usr/bin/time -v timeout 900 python bench.py > gpurun_out/bench_default_final.log 2> gpurun_out/bench_default_final.err; tail -1 gpurun_out/bench_default_final.log; grep -E "Elapsed|Maximum resident" gpurun_out/bench_default_final.err
+B="python bench.py --qubits 28 --depth 20 --steps 1 --warmup 1 --no-cpu-baseline"
+timeout 300 $B > gpurun_out/ncu_plain2.log 2>&1 && timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r1_launches_brickwork28q_final.csv $B > gpurun_out/ncu_launches2.log 2>&1
+wc -l gpurun_out/r1_launches_brickwork28q_final.csv
