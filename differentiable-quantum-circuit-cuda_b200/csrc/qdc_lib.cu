@@ -182,6 +182,15 @@ QDC_EXPORT const char* qdc_circuit_last_profile(const qdc_circuit* c, int cat, q
 //   [type, inst, p2, p1, gbit, lpos, count, nbits] then, for TILE steps,
 //   count x [inst, p2, p1] followed by nbits x [physical bit].
 // After the last step: [-1, n, final_map[0..n-1]].
+static int g_schedule_tile_strategy = -1;  // < 0: the library default
+
+// Tiling strategy used by the following qdc_schedule() calls (0 first-fit, 1 window growth, 2 + look-ahead;
+// < 0 restores the default).  Lets the CPU suite check every strategy without a device.
+QDC_EXPORT const char* qdc_schedule_set_strategy(int tile_strategy) {
+  g_schedule_tile_strategy = tile_strategy;
+  return nullptr;
+}
+
 QDC_EXPORT const char* qdc_schedule(size_t n, size_t n_loc, int tile_bits, int low_bits, int max_tile_gates,
                                     const int* kinds, const size_t* pos2, const size_t* pos1, size_t count,
                                     int all_densities, int64_t* out, size_t cap, size_t* out_len) {
@@ -200,6 +209,7 @@ QDC_EXPORT const char* qdc_schedule(size_t n, size_t n_loc, int tile_bits, int l
   so.tile_bits = tile_bits;
   so.low_bits = low_bits;
   if (max_tile_gates > 0) so.max_tile_gates = max_tile_gates;
+  if (g_schedule_tile_strategy >= 0) so.tile_strategy = g_schedule_tile_strategy;
   qdc::Scheduler sch(si, so);
   const qdc::Plan plan = sch.run();
   std::vector<int64_t> enc;

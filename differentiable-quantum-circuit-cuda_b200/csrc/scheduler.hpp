@@ -80,7 +80,8 @@ struct SchedOptions {
   int swap_min_pos = 4;
   // Tiling strategy: 1 = grow each tile as a window around a seed gate (a gate joins only when it needs no new
   // position; when nothing more fits, the candidate needing the fewest new positions, closest to the window,
-  // is admitted) -- light-cone triangles / diamonds over contiguous qubits; 0 = first-fit in program order
+  // is admitted) -- light-cone triangles / diamonds over contiguous qubits; 2 = the same with a look-ahead
+  // (the candidate that lets the most gates in per new position); 0 = first-fit in program order
   // (scatters a tile's positions over unrelated pairs: 7.5 gates per pass on 32-qubit brickwork against
   // ~2x that for windows).
   int tile_strategy = 1;
@@ -185,7 +186,7 @@ class Scheduler {
       std::vector<int> bits;  // high bits (>= low_bits) of the open tile
       std::vector<Step> in_tile, deferred;
       const int cap = o_.tile_bits - o_.low_bits;
-      if (o_.tile_strategy == 1) {
+      if (o_.tile_strategy >= 1) {
         if (!tileable(pending[0])) {  // a density / global-diagonal at the head runs on its own
           plan.steps.push_back(pending[0]);
           pending.erase(pending.begin());
@@ -264,6 +265,39 @@ class Scheduler {
     grow_window(pending, cap, o_.low_bits, o_.max_tile_gates, bits, in_tile, deferred);
   }
 
+  // Number of still unchosen gates a window over `wbits` would admit (closure under the admission rule).
+  int closure_gain(const std::vector<Step>& pending, const std::vector<char>& chosen0, const std::vector<int>& wbits,
+                   int free_below, int limit) const {
+    const int M = (int)pending.size();
+    std::vector<char> chosen(chosen0), dirty(o_.n);
+    auto has = [&](int p) { return p < 0 || p < free_below || std::find(wbits.begin(), wbits.end(), p) != wbits.end(); };
+    int gain = 0;
+    for (bool progress = true; progress && gain < limit;) {
+      progress = false;
+      std::fill(dirty.begin(), dirty.end(), 0);
+      for (int k = 0; k < M && gain < limit; k++) {
+        if (chosen[k]) continue;
+        const Step& st = pending[k];
+        if (!tileable(st)) {
+          if (st.type == ST_DENS) break;
+          if (st.p2 >= 0 && st.p2 < o_.n) dirty[st.p2] = 1;
+          if (st.p1 >= 0 && st.p1 < o_.n) dirty[st.p1] = 1;
+          continue;
+        }
+        const bool dep = dirty[st.p2] || (st.p1 >= 0 && dirty[st.p1]);
+        if (!dep && has(st.p2) && has(st.p1)) {
+          chosen[k] = 1;
+          gain++;
+          progress = true;
+        } else {
+          dirty[st.p2] = 1;
+          if (st.p1 >= 0) dirty[st.p1] = 1;
+        }
+      }
+    }
+    return gain;
+  }
+
   // `free_below`: positions below it are always available (the tile's forced low positions) and do not count.
   void grow_window(const std::vector<Step>& pending, int cap, int free_below, int max_gates, std::vector<int>& bits,
                    std::vector<Step>& in_tile, std::vector<Step>& deferred) {
@@ -273,10 +307,13 @@ class Scheduler {
     auto has = [&](int p) { return p < 0 || p < free_below || std::find(bits.begin(), bits.end(), p) != bits.end(); };
     auto extra_of = [&](const Step& st) { return (has(st.p2) ? 0 : 1) + ((st.p1 == st.p2 || has(st.p1)) ? 0 : 1); };
     std::vector<char> dirty(o_.n);
+    struct Cand { int k, extra, dist; };
+    std::vector<Cand> cands;
     for (;;) {
       // sweep: admit everything that needs no new position; remember the best candidate that does
       bool progress = false;
       int best = -1, best_extra = 0, best_dist = 0;
+      cands.clear();
       std::fill(dirty.begin(), dirty.end(), 0);
       bool wall = false;  // a density / non-tileable step ahead blocks everything behind it
       for (int k = 0; k < M && !wall && nchosen < max_gates; k++) {
@@ -310,12 +347,34 @@ class Scheduler {
             best_extra = extra;
             best_dist = dist;
           }
+          if (o_.tile_strategy >= 2) cands.push_back(Cand{k, extra, dist});
         }
         dirty[st.p2] = 1;
         if (st.p1 >= 0) dirty[st.p1] = 1;
       }
       if (progress) continue;  // newly admitted gates may have unblocked others
       if (best < 0 || nchosen >= max_gates) break;
+      if (o_.tile_strategy >= 2 && cands.size() > 1) {
+        // look-ahead: admit the candidate whose positions let the most gates in per new position
+        // (grows a window towards fresh work instead of into qubits that are already ahead in time)
+        std::sort(cands.begin(), cands.end(), [](const Cand& a, const Cand& b) {
+          return a.dist != b.dist ? a.dist < b.dist : a.k < b.k;
+        });
+        if (cands.size() > 8) cands.resize(8);
+        double best_score = -1;
+        for (const Cand& c : cands) {
+          std::vector<int> trial = bits;
+          const Step& cs = pending[c.k];
+          if (!has(cs.p2)) trial.push_back(cs.p2);
+          if (!has(cs.p1) && cs.p1 != cs.p2) trial.push_back(cs.p1);
+          const int gain = closure_gain(pending, chosen, trial, free_below, max_gates - nchosen);
+          const double score = (double)gain / c.extra;
+          if (score > best_score + 1e-9) {
+            best_score = score;
+            best = c.k;
+          }
+        }
+      }
       const Step& st = pending[best];
       if (!has(st.p2)) bits.push_back(st.p2);
       if (!has(st.p1)) bits.push_back(st.p1);
@@ -335,7 +394,7 @@ class Scheduler {
       std::vector<int> bits;
       std::vector<Step> grp, deferred;
       std::vector<bool> dirty(o_.n, false);
-      if (o_.tile_strategy == 1) {
+      if (o_.tile_strategy >= 1) {
         // same window growth as for the tiles: 3.6 instead of 3.0 gates per register block on brickwork
         grow_window(pending, RB, 0, 1 << 30, bits, grp, deferred);
         pending.clear();

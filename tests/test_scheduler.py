@@ -65,9 +65,10 @@ def reference_results(o, const, var):
     return dens, cts_conj, grads
 
 
-def check_plan(pkg, o, const, var, n, n_loc, tile_bits, low_bits, max_tile_gates=0):
+def check_plan(pkg, o, const, var, n, n_loc, tile_bits, low_bits, max_tile_gates=0, tile_strategy=-1):
     dens_ref, cts_conj, grads_ref = reference_results(o, const, var)
-    enc = pkg._ffi.schedule(o.instructions, n, n_loc, tile_bits, low_bits, max_tile_gates)
+    enc = pkg._ffi.schedule(o.instructions, n, n_loc, tile_bits, low_bits, max_tile_gates,
+                            tile_strategy=tile_strategy)
     steps, final_map = op.decode_plan(enc)
     # structure
     seen = []
@@ -141,6 +142,33 @@ def test_brickwork_swap_count_follows_the_light_cone(pkg):
     gates = sum(1 for st in steps if st["type"] == op.ST_GATE)
     assert gates == 1700
     assert swaps <= 40, swaps
+
+
+@pytest.mark.parametrize("case", ["brickwork", "vqse", "autodiff"])
+@pytest.mark.parametrize("strategy", [0, 1, 2])
+@pytest.mark.parametrize("g", [0, 2])
+def test_every_tiling_strategy_is_exact(pkg, case, strategy, g):
+    """First-fit, window growth and window growth with look-ahead (scheduler.hpp: tile_strategy) all
+    reproduce the program-order densities and gradients, single GPU and sharded over 4 ranks."""
+    n = 9
+    o, const, var = make_case(case, n, np.random.default_rng(6))
+    check_plan(pkg, o, const, var, n, n - g, 5, 2, tile_strategy=strategy)
+
+
+def test_window_tiling_halves_the_passes_of_a_brickwork_circuit(pkg):
+    """32 qubits, depth 100, 2^12 tiles with 4 forced low positions: first-fit in program order scatters a
+    tile's positions over unrelated pairs (207 passes); windows hold light-cone strips of 8 qubits."""
+    o = OracleCircuit.__new__(OracleCircuit)
+    o.instructions = []
+    brickwork(o, 32, 100)
+    passes = {}
+    for strategy in (0, 1, 2):
+        enc = pkg._ffi.schedule(o.instructions, 32, 32, 12, 4, 32, tile_strategy=strategy)
+        steps, _ = op.decode_plan(enc)
+        tiles = [st for st in steps if st["type"] == op.ST_TILE]
+        assert sum(len(t["gates"]) for t in tiles) + sum(1 for st in steps if st["type"] == op.ST_GATE) == 1550
+        passes[strategy] = len(tiles)
+    assert passes[1] <= 0.55 * passes[0] and passes[2] <= passes[1], passes
 
 
 def test_remap_victims_avoid_short_run_positions(pkg):
