@@ -455,7 +455,7 @@ def main():
     ap.add_argument("--soa", type=int, default=1, help="f32 tile kernels: 1 pair-lane smem layout, 0 interleaved layout")
     ap.add_argument("--rb-policy", type=int, default=-1, help="fuse=2 forward: 0 never register-block, 1 always, 2 by gate mix (default)")
     ap.add_argument("--batch-dens", type=int, default=-1, help="0: one sweep per density / seed")
-    ap.add_argument("--tile-strategy", type=int, default=-1, help="scheduler tiling: 1 window growth (default), 0 first-fit")
+    ap.add_argument("--tile-strategy", type=int, default=-1, help="scheduler tiling: 2 window growth with look-ahead (default), 1 window growth, 0 first-fit")
     ap.add_argument("--stagger", type=int, default=-1, help="CTA start skew, percent of the library default (0: off)")
     ap.add_argument("--tile-debug", type=int, default=0, help="profiling aid (1: no HBM traffic, 2: no gates); invalid results")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -211,7 +211,7 @@ class Circuit {
   cudaStream_t stream_ = 0;
   Stats stats_;
   int opt_fuse_ = 2;          // 0: one pass per instruction, 1: tiled multi-gate passes, 2: + register-blocked forward
-  int opt_tile_strategy_ = 1;  // scheduler.hpp: 1 window growth, 0 first-fit tiling
+  int opt_tile_strategy_ = 2;  // scheduler.hpp: 2 window growth with look-ahead, 1 window growth, 0 first-fit tiling
   int opt_batch_dens_ = 1;    // 1: densities / density seeds of one program point share tiled sweeps (tile_dens_kernels.cuh)
   int opt_soa_ = 1;           // f32 tile kernels: 1 pair-lane shared-memory layout (tile_soa_kernels.cuh), 0 interleaved
   int opt_tile_bits_ = 0;  // 0: default for the precision

@@ -84,7 +84,7 @@ struct SchedOptions {
   // (the candidate that lets the most gates in per new position); 0 = first-fit in program order
   // (scatters a tile's positions over unrelated pairs: 7.5 gates per pass on 32-qubit brickwork against
   // ~2x that for windows).
-  int tile_strategy = 1;
+  int tile_strategy = 2;
 };
 
 class Scheduler {
