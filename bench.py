@@ -225,6 +225,8 @@ def run_ours(args):
         from importlib import import_module
         sharded = import_module("differentiable-quantum-circuit-cuda_b200.sharded")
         circ = sharded.ShardedCircuit(n_total, precision=args.precision)
+    elif args.fusion:
+        circ = pkg.FusedCircuit(n_total, precision=args.precision)
     else:
         circ = pkg.Circuit(n_total, precision=args.precision)
     circ.set_option("fuse", args.fuse)
@@ -363,6 +365,7 @@ def run_ours(args):
                    "l2": "inputs (state + adjoint) far larger than L2; no flush needed",
                    "exchange": (("peer-memory swap kernel (NVLink, CUDA IPC)" if circ.peer_exchange else
                                  "NCCL send/recv + pack/unpack") if world > 1 else None),
+                   "gate_fusion": bool(args.fusion and world == 1),
                    "executor": ["one pass per gate", "tiled multi-gate passes",
                                 "tiled multi-gate passes, forward kernel (register-blocked or per gate) by gate mix"][args.fuse]
                                + (", pair-lane smem layout" if args.precision == "f32" and args.soa and args.fuse else "")},
@@ -453,6 +456,7 @@ def main():
     ap.add_argument("--max-tile-gates", type=int, default=0)
     ap.add_argument("--peer", type=int, default=1, help="sharded: 1 peer-memory swap kernel, 0 NCCL send/recv")
     ap.add_argument("--soa", type=int, default=1, help="f32 tile kernels: 1 pair-lane smem layout, 0 interleaved layout")
+    ap.add_argument("--fusion", type=int, default=0, help="1: FusedCircuit (host-side gate fusion + gradient chain rule)")
     ap.add_argument("--rb-policy", type=int, default=-1, help="fuse=2 forward: 0 never register-block, 1 always, 2 by gate mix (default)")
     ap.add_argument("--batch-dens", type=int, default=-1, help="0: one sweep per density / seed")
     ap.add_argument("--tile-strategy", type=int, default=-1, help="scheduler tiling: 2 window growth with look-ahead (default), 1 window growth, 0 first-fit")

@@ -23,6 +23,7 @@ from . import state_io
 from .quantized_tensor import QuantizedTensor, get_q1_grad, get_q2_grad, get_q2_grad_diag, data_transfer
 from . import quantum_differentiable_circuit as _qdc_native
 from . import qdc as _qdc_py
+from .fusion import FusedCircuit
 
 _sys.modules.setdefault("quantum_differentiable_circuit", _qdc_native)
 _sys.modules.setdefault("qdc", _qdc_py)
@@ -31,6 +32,6 @@ Circuit = _qdc_native.Circuit
 AutoGradCircuit = _qdc_py.AutoGradCircuit
 
 __all__ = [
-    "Circuit", "AutoGradCircuit", "QuantizedTensor", "get_q1_grad", "get_q2_grad", "get_q2_grad_diag",
+    "Circuit", "FusedCircuit", "AutoGradCircuit", "QuantizedTensor", "get_q1_grad", "get_q2_grad", "get_q2_grad_diag",
     "data_transfer", "common_gates", "state_io", "QdcError", "get_lib", "lib_path",
 ]
