@@ -336,6 +336,10 @@ static inline const char* rb_make_groups(const qdc::Plan& plan, const qdc::Step&
                                          int T, const std::vector<Inst>& insts, RbGroup* grp, int* ngroups,
                                          std::vector<int>* code_of, std::vector<bool>* swap_of) {
   if (t.grp_count > QDC_RB_MAXGRP) return qdc_errf("tile pass holds too many register-block groups.");
+  // the kernels give every thread of the CTA its own 2^4-amplitude block per sweep: fewer blocks than threads
+  // would make threads share blocks (make_tile_geo keeps tiles at >= 2^11 amplitudes for this reason)
+  if ((1 << (T - QDC_RB)) < QDC_TILE_NT_F || (1 << (T - QDC_RB)) < QDC_TILE_NT_BRB)
+    return qdc_errf("tile of 2^%d amplitudes is too small for the register-blocked kernels.", T);
   *ngroups = t.grp_count;
   code_of->assign(t.count, -1);
   swap_of->assign(t.count, false);
