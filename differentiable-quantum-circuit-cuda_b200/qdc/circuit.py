@@ -136,9 +136,14 @@ def _torch_apply(run: _AutodiffRun, var_gates, const_gates):
 
 class AutoGradCircuit:
 
-    def __init__(self, qubits_number: int, precision: str | None = None):
-        """Quantum circuit with automatic differentiation (src/qdc/circuit.py:10-12)."""
-        self.circuit = Circuit(qubits_number, precision=precision)
+    def __init__(self, qubits_number: int, precision: str | None = None, fused: bool = False):
+        """Quantum circuit with automatic differentiation (src/qdc/circuit.py:10-12).  `fused=True` puts
+        host-side gate fusion in front of the executor (fusion.py; opt-in, not in the reference)."""
+        if fused:
+            from ..fusion import FusedCircuit
+            self.circuit = FusedCircuit(qubits_number, precision=precision)
+        else:
+            self.circuit = Circuit(qubits_number, precision=precision)
 
     def set_state_from_vector(self, vec):
         """Set initial state from an array (src/qdc/circuit.py:14-22)."""
