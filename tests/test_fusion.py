@@ -133,3 +133,27 @@ def test_fused_circuit_on_the_gpu_matches_the_oracle(precision):
         grads_f = f.backward([np.asarray(ct, dtype=dtype).conj() for ct in cts], const, var)
         scale = max(np.abs(g).max() for g in grads_o)
         assert max(np.abs(a - b).max() for a, b in zip(grads_f, grads_o)) / scale < tol
+
+
+@pytest.mark.gpu
+def test_autograd_circuit_with_fusion_matches_the_plain_one():
+    """qdc.AutoGradCircuit(fused=True): same densities and vjp as the unfused wrapper (f64, VQSE ansatz)."""
+    from qdc import AutoGradCircuit
+    n, layers = 12, 2
+    rng = np.random.default_rng(12)
+    res = {}
+    o = OracleCircuit(n)
+    vqse(o, n, layers)
+    _, var = _gates_for(o, rng)
+    for fused in (False, True):
+        c = AutoGradCircuit(n, precision="f64", fused=fused)
+        vqse(c, n, layers)
+        simple_run, autodiff_run = c.build()
+        dens = autodiff_run.forward(var, [])
+        _, cts = tsallis_loss_and_cotangents(dens)
+        res[fused] = (dens, autodiff_run.vjp(var, [], cts), simple_run(var, []))
+    for a, b in zip(res[True][0] + res[True][2], res[False][0] + res[False][2]):
+        np.testing.assert_allclose(a, b, atol=1e-12)
+    scale = max(np.abs(g).max() for g in res[False][1])
+    for a, b in zip(res[True][1], res[False][1]):
+        np.testing.assert_allclose(a, b, atol=1e-11 * scale)
