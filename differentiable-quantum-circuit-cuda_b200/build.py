@@ -45,22 +45,31 @@ def lib_path(precision: str) -> str:
     return os.path.join(LIB, f"libqdc_b200_{precision}.so")
 
 
+def _build_one(precision, defs, force, verbose):
+    out = lib_path(precision)
+    stamp = out + ".sha256"
+    digest = _digest(" ".join(FLAGS + defs))
+    if not force and os.path.exists(out) and os.path.exists(stamp):
+        with open(stamp) as f:
+            if f.read().strip() == digest:
+                return
+    cmd = [NVCC] + FLAGS + defs + ["-o", out, os.path.join(CSRC, "qdc_lib.cu")]
+    if verbose:
+        print("[build]", " ".join(cmd), flush=True)
+    subprocess.run(cmd, check=True, cwd=CSRC)
+    with open(stamp, "w") as f:
+        f.write(digest)
+
+
 def build(force: bool = False, verbose: bool = True) -> None:
+    """Both precision builds, side by side (each is one ~3 minute nvcc translation unit)."""
+    from concurrent.futures import ThreadPoolExecutor
     os.makedirs(LIB, exist_ok=True)
-    for precision, defs in (("f32", []), ("f64", ["-DQDC_F64"])):
-        out = lib_path(precision)
-        stamp = out + ".sha256"
-        digest = _digest(" ".join(FLAGS + defs))
-        if not force and os.path.exists(out) and os.path.exists(stamp):
-            with open(stamp) as f:
-                if f.read().strip() == digest:
-                    continue
-        cmd = [NVCC] + FLAGS + defs + ["-o", out, os.path.join(CSRC, "qdc_lib.cu")]
-        if verbose:
-            print("[build]", " ".join(cmd), flush=True)
-        subprocess.run(cmd, check=True, cwd=CSRC)
-        with open(stamp, "w") as f:
-            f.write(digest)
+    with ThreadPoolExecutor(2) as ex:
+        futs = [ex.submit(_build_one, precision, defs, force, verbose)
+                for precision, defs in (("f32", []), ("f64", ["-DQDC_F64"]))]
+        for f in futs:
+            f.result()
 
 
 if __name__ == "__main__":
