@@ -157,3 +157,32 @@ def test_autograd_circuit_with_fusion_matches_the_plain_one():
     scale = max(np.abs(g).max() for g in res[False][1])
     for a, b in zip(res[True][1], res[False][1]):
         np.testing.assert_allclose(a, b, atol=1e-11 * scale)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_programs_fuse_exactly(seed):
+    """Random programs over every instruction kind: fused program + chain rule == original (oracle VM)."""
+    from test_scheduler import _random_program
+    rng = np.random.default_rng(200 + seed)
+    n = 6
+    o, const, var = _random_program(rng, n, 50)
+    f = fusion.FusedCircuit(n, backend=lambda q: OracleCircuit(q))
+    adders = {0: "add_q2_const_gate", 1: "add_q2_var_gate", 2: "add_q2_const_gate_nonu", 3: "add_q2_var_gate_nonu",
+              4: "add_q2_const_gate_diag", 5: "add_q2_var_gate_diag", 6: "add_q1_const_gate",
+              7: "add_q1_const_gate_nonu", 8: "add_q1_var_gate", 9: "add_q1_var_gate_nonu", 10: "get_q2_dens_op",
+              11: "get_q1_dens_op", 12: "get_q2_dens_op_with_grad", 13: "get_q1_dens_op_with_grad"}
+    for inst in o.instructions:
+        getattr(f, adders[inst[0]])(*inst[1:])
+    dens_o, dens_f = o.forward(const, var), f.forward(const, var)
+    for a, b in zip(dens_f, dens_o):
+        np.testing.assert_allclose(a, b, atol=1e-11)
+    cts = []
+    for d in dens_o:
+        a = rng.normal(size=d.shape) + 1j * rng.normal(size=d.shape)
+        cts.append((a + a.conj().T) / 2)
+    grads_o = vjp(o, var, const, cts)
+    grads_f = f.backward([ct.conj() for ct in cts], const, var)
+    scale = max([np.abs(g).max() for g in grads_o] + [1e-30])
+    for a, b in zip(grads_f, grads_o):
+        np.testing.assert_allclose(a, b, atol=1e-10 * scale)
+    assert f.fused_gate_count <= sum(1 for i in o.instructions if i[0] < 10)
