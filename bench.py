@@ -171,10 +171,8 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------ CPU baseline
-def cpu_baseline(n_target, budget_s=12.0):
-    """The oracle (NumPy port of the path) timed on the host: fwd+bwd of the same
-    brickwork pattern on a reduced register (the 2^32-amplitude state does not fit
-    a bounded CPU run), scaled to the target size by the amplitude ratio."""
+def _cpu_baseline_numpy(budget_s):
+    """The oracle (NumPy port of the path) on one core: fwd+bwd of brickwork gates at 22 qubits."""
     from oracle import statevector as sv
     n = 22
     rng = np.random.default_rng(1234)
@@ -195,10 +193,57 @@ def cpu_baseline(n_target, budget_s=12.0):
         sv.q2grad(psi, bwd, p2, p1)
         bwd = sv.q2gate_fast(bwd, sv.q2_tr(g), p2, p1)
     dt = time.perf_counter() - t0
-    rate_small = done / dt
-    return {"value": rate_small * 2.0 ** (n - n_target), "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": f"oracle (NumPy) fwd+bwd of {done} brickwork gates at {n} qubits complex64 in {dt:.1f}s "
-                      f"= {rate_small:.3g} gate-applies/s, scaled by 2^({n}-{n_target}) amplitudes"}
+    return n, done, dt
+
+
+def _cpu_baseline_torch(budget_s):
+    """The same algorithm (apply / un-compute with U^dagger / gradient outer product / pull back with U^T) as
+    batched 4x4 matmuls on torch CPU tensors with all host threads: fwd+bwd of brickwork gates at 24 qubits."""
+    import torch
+    n = 24
+    rng = np.random.default_rng(1234)
+    gates, _ = brickwork_program(n, 2)
+    mats = [torch.tensor(haar(rng, 4).reshape(4, 4), dtype=torch.complex64) for _ in gates]
+    psi = torch.zeros(1 << n, dtype=torch.complex64)
+    psi[0] = 1
+
+    def apply(x, g, lo):   # adjacent pair (lo + 1, lo): index = 2 bit(lo + 1) + bit(lo)
+        return torch.matmul(g, x.view(1 << (n - lo - 2), 4, 1 << lo)).reshape(-1)
+
+    t0 = time.perf_counter()
+    done = 0
+    for (p2, p1), g in zip(gates, mats):
+        psi = apply(psi, g, p1)
+        done += 1
+        if time.perf_counter() - t0 > budget_s / 4:
+            break
+    bwd = 2 * psi.conj()
+    for (p2, p1), g in list(zip(gates, mats))[:done][::-1]:
+        psi = apply(psi, g.conj().T.contiguous(), p1)
+        torch.einsum("apc,aqc->pq", bwd.view(1 << (n - p1 - 2), 4, 1 << p1), psi.view(1 << (n - p1 - 2), 4, 1 << p1))
+        bwd = apply(bwd, g.T.contiguous(), p1)
+    dt = time.perf_counter() - t0
+    return n, done, dt, torch.get_num_threads()
+
+
+def cpu_baseline(n_target, budget_s=12.0):
+    """CPU restatements of the path timed on the host (the reference has no CPU implementation): the NumPy oracle
+    on one core and a torch port on all host threads, each on a reduced register (the 2^32-amplitude state does not
+    fit a bounded CPU run), scaled to the target size by the amplitude ratio.  The faster one is reported."""
+    n1, done1, dt1 = _cpu_baseline_numpy(budget_s)
+    r1 = done1 / dt1 * 2.0 ** (n1 - n_target)
+    note1 = (f"oracle (NumPy, 1 core) fwd+bwd of {done1} brickwork gates at {n1} qubits complex64 in {dt1:.1f}s "
+             f"= {done1 / dt1:.3g} gate-applies/s")
+    try:
+        n2, done2, dt2, threads = _cpu_baseline_torch(budget_s)
+        r2 = done2 / dt2 * 2.0 ** (n2 - n_target)
+        note2 = (f"torch-CPU port ({threads} threads of {os.cpu_count()} cores) fwd+bwd of {done2} brickwork gates at "
+                 f"{n2} qubits complex64 in {dt2:.1f}s = {done2 / dt2:.3g} gate-applies/s")
+    except Exception as e:  # noqa: BLE001
+        r2, threads, note2 = 0.0, 1, f"torch-CPU port failed: {e}"
+    best, cores = (r2, threads) if r2 > r1 else (r1, 1)
+    return {"value": best, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{note2}; {note1}; both scaled by the amplitude ratio to {n_target} qubits, the faster reported"}
 
 
 # ------------------------------------------------------------------- arms
