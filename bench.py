@@ -178,7 +178,7 @@ def _cpu_baseline_numpy(budget_s):
     rng = np.random.default_rng(1234)
     dtype = np.complex64
     psi = sv.standard_state(n, dtype)
-    gates, _ = brickwork_program(n, 2)
+    gates, _ = brickwork_program(n, 8)    # the forward loop stops at budget / 3
     mats = [haar(rng, 4).astype(dtype) for _ in gates]
     t0 = time.perf_counter()
     done = 0
@@ -202,7 +202,7 @@ def _cpu_baseline_torch(budget_s):
     import torch
     n = 24
     rng = np.random.default_rng(1234)
-    gates, _ = brickwork_program(n, 2)
+    gates, _ = brickwork_program(n, 40)   # more than the time budget admits: the forward loop stops at budget / 4
     mats = [torch.tensor(haar(rng, 4).reshape(4, 4), dtype=torch.complex64) for _ in gates]
     psi = torch.zeros(1 << n, dtype=torch.complex64)
     psi[0] = 1
