@@ -196,6 +196,12 @@ def _cpu_baseline_numpy(budget_s):
     return n, done, dt
 
 
+def _torch_apply_adjacent(x, g, lo, n):
+    """q2 gate (4x4 torch tensor, reference index convention) on the adjacent pair (lo + 1, lo) of a torch state."""
+    import torch
+    return torch.matmul(g, x.view(1 << (n - lo - 2), 4, 1 << lo)).reshape(-1)
+
+
 def _cpu_baseline_torch(budget_s):
     """The same algorithm (apply / un-compute with U^dagger / gradient outer product / pull back with U^T) as
     batched 4x4 matmuls on torch CPU tensors with all host threads: fwd+bwd of brickwork gates at 24 qubits."""
@@ -207,8 +213,8 @@ def _cpu_baseline_torch(budget_s):
     psi = torch.zeros(1 << n, dtype=torch.complex64)
     psi[0] = 1
 
-    def apply(x, g, lo):   # adjacent pair (lo + 1, lo): index = 2 bit(lo + 1) + bit(lo)
-        return torch.matmul(g, x.view(1 << (n - lo - 2), 4, 1 << lo)).reshape(-1)
+    def apply(x, g, lo):
+        return _torch_apply_adjacent(x, g, lo, n)
 
     t0 = time.perf_counter()
     done = 0

@@ -271,3 +271,22 @@ def test_oracle_matches_reference_cuda_golden_vectors():
     B200 by tests/golden/make_golden.py; the oracle must reproduce them."""
     from golden.replay_golden import check_oracle_against_golden
     check_oracle_against_golden(GOLDEN)
+
+
+def test_bench_torch_cpu_port_matches_the_oracle():
+    """bench.py's multi-core CPU baseline applies gates as batched 4x4 matmuls: same result as the oracle."""
+    import importlib
+    import torch
+    from oracle import statevector as sv
+    bench = importlib.import_module("bench")
+    n = 7
+    rng = np.random.default_rng(3)
+    psi = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
+    g = bench.haar(rng, 4)
+    for lo in (0, 2, 5):
+        want = sv.q2gate(psi, g, lo + 1, lo)
+        got = bench._torch_apply_adjacent(torch.tensor(psi), torch.tensor(g.reshape(4, 4)), lo, n).numpy()
+        np.testing.assert_allclose(got, want, atol=1e-12)
+        grad = torch.einsum("apc,aqc->pq", torch.tensor(want).view(1 << (n - lo - 2), 4, 1 << lo),
+                            torch.tensor(psi).view(1 << (n - lo - 2), 4, 1 << lo)).numpy().reshape(-1)
+        np.testing.assert_allclose(grad, sv.q2grad(psi, want, lo + 1, lo), atol=1e-11)
