@@ -23,13 +23,17 @@ FLAGS = [
     "-O3", "-lineinfo", "-std=c++17",
     "-shared", "-Xcompiler", "-fPIC,-fvisibility=hidden",
     "-Xlinker", "-Bsymbolic",
+    # only the C ABI is exported (weak libstdc++ instantiations stay local)
+    "-Xlinker", "--version-script=" + os.path.join(CSRC, "qdc_exports.map"),
+    # dynamic CUDA runtime: the static one embeds the names of every runtime entry point
+    "-cudart", "shared", "-Xlinker", "-rpath=/usr/local/cuda/lib64",
     "--extended-lambda",
 ]
 
 
 def _sources():
     return sorted(
-        os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".hpp", ".h"))
+        os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".hpp", ".h", ".map"))
     )
 
 

@@ -202,6 +202,7 @@ class Circuit {
   cplx_t* peer_state_[kMaxWorld] = {nullptr};
   cplx_t* peer_bwd_[kMaxWorld] = {nullptr};
   bool peer_ok_ = false;
+  std::string peer_fail_;     // why the CUDA IPC mapping failed (reported by exchange() unless peer = 0)
   int opt_peer_ = 1;          // 1: peer-memory swap kernel when available, 0: NCCL send/recv + pack/unpack
   int* d_token_ = nullptr;    // 2 ints: tokens of the stream-ordered pairwise barriers
   Workspace ws_;
@@ -226,6 +227,7 @@ class Circuit {
   bool plan_all_dens_ = false;
   std::vector<int> exec_p2_, exec_p1_;  // physical positions each instruction ran at
   std::vector<int> cur_map_;            // logical qubit -> physical position of state_ right now (empty: identity)
+  bool forward_valid_ = false;          // state_ holds the result of forward() of the CURRENT program
 
   void release() {
     if (state_) cudaFree(state_);
@@ -265,6 +267,10 @@ class Circuit {
     int g = 0;
     while ((1 << g) < world) g++;
     if (g >= n_) return qdc_errf("more ranks than amplitudes.");
+    // a dense two-qubit gate needs two local positions, and the exchange / streaming launchers split
+    // the shard by vectors of 2^QDC_LV amplitudes
+    if (world > 1 && n_ - g < 2 + QDC_LV)
+      return qdc_errf("too many ranks: %d local qubits per rank, at least %d are needed.", n_ - g, 2 + QDC_LV);
     if (state_) QDC_CUDA(cudaFree(state_));
     state_ = nullptr;
     if (bwd_) QDC_CUDA(cudaFree(bwd_));
@@ -294,11 +300,15 @@ class Circuit {
   // leaves the NCCL send/recv path in charge.
   void setup_peers() {
     peer_ok_ = false;
-    if (world_ > kMaxWorld) return;
+    peer_fail_ = "the partner buffers could not be exchanged or mapped";
+    if (world_ > kMaxWorld) {
+      peer_fail_ = "world size above the peer table";
+      return;
+    }
     struct Handles { cudaIpcMemHandle_t s, b; };
     Handles mine;
     if (cudaIpcGetMemHandle(&mine.s, state_) != cudaSuccess || cudaIpcGetMemHandle(&mine.b, bwd_) != cudaSuccess) {
-      cudaGetLastError();
+      peer_fail_ = std::string("cudaIpcGetMemHandle: ") + cudaGetErrorName(cudaGetLastError());
       return;
     }
     Handles *d_mine = nullptr, *d_all = nullptr;
@@ -317,7 +327,7 @@ class Circuit {
       void *ps = nullptr, *pb = nullptr;
       if (cudaIpcOpenMemHandle(&ps, all[p].s, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
           cudaIpcOpenMemHandle(&pb, all[p].b, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
-        cudaGetLastError();
+        peer_fail_ = std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorName(cudaGetLastError());
         mapped = 0;
         break;
       }
@@ -336,6 +346,8 @@ class Circuit {
       cudaFree(d_flag);
     }
     peer_ok_ = (total == 0);
+    if (peer_ok_) peer_fail_.clear();
+    else if (mapped) peer_fail_ = "the mapping failed on another rank";
   }
 
   const char* ensure_results(size_t slots) {
@@ -353,6 +365,7 @@ class Circuit {
     if (len == 0 || (len & (len - 1)) != 0) return qdc_errf("State size is not a power of 2.");
     if (len != ((size_t)1 << n_loc_))
       return qdc_errf("Size of the given state does not match the size of the tensor.");
+    forward_valid_ = false;
     if (!initial_) QDC_CUDA(cudaMalloc((void**)&initial_, bytes()));
     QDC_CUDA(cudaMemcpy(initial_, host, bytes(), cudaMemcpyHostToDevice));
     return nullptr;
@@ -369,6 +382,7 @@ class Circuit {
       if (pos2 >= (size_t)n_) return qdc_errf("pos2 is out of the bound.");
     }
     insts_.push_back(Inst{kind, (int)pos2, one ? -1 : (int)pos1});
+    forward_valid_ = false;
     return nullptr;
   }
 
@@ -507,6 +521,7 @@ class Circuit {
   // Load this rank's shard as the INITIAL state of the circuit (the role of
   // set_state_from_vector).  The file must be in the identity layout.
   const char* load_state(const char* path) {
+    forward_valid_ = false;
     FILE* f = fopen(path, "rb");
     if (!f) return qdc_errf("cannot open %s for reading.", path);
     StateHeader h;
@@ -739,6 +754,11 @@ class Circuit {
 
   const char* exchange(cplx_t* buf, int gbit, int lpos) {
     if (peer_ok_ && opt_peer_) return exchange_peer(buf, gbit, lpos);
+    // No silent performance cliff (the NCCL path runs at ~2/3 of the peer kernel's rate and needs 2 x half a
+    // shard of staging): falling back is the caller's decision, option peer = 0.
+    if (opt_peer_)
+      return qdc_errf("peer-memory exchange unavailable (%s); set option \"peer\" to 0 for the NCCL send/recv exchange.",
+                      peer_fail_.c_str());
     QDC_TRY(ensure_staging());
     const int c = (rank_ >> gbit) & 1, partner = rank_ ^ (1 << gbit);
     const size_t half_bytes = bytes() / 2;
@@ -773,11 +793,16 @@ class Circuit {
     if (cap < need) return qdc_errf("Output buffer too small: %zu < %zu.", cap, need);
     const size_t nslots = count(all_dens ? 3 : 4);
     QDC_TRY(ensure_results(nslots));
+    forward_valid_ = false;
     build_plan(all_dens);
+    if (!plan_.ok)
+      return qdc_errf("the program cannot be scheduled on %d local qubits per rank (an instruction never has all "
+                      "its qubits local).", n_loc_);
     QDC_TRY(reset_state());
     if (nslots) QDC_CUDA(cudaMemsetAsync(d_res_, 0, nslots * 32 * sizeof(double), stream_));
     QDC_TRY(run_forward(gp, all_dens));
     cur_map_ = plan_.final_map;
+    forward_valid_ = true;
     // single read-back of every density
     if (nslots) {
       QDC_CUDA(cudaMemcpyAsync(h_res_.data(), d_res_, nslots * 32 * sizeof(double), cudaMemcpyDeviceToHost,
@@ -890,7 +915,11 @@ class Circuit {
   const char* backward(const GateList& dg, const GateList& cg, const GateList& vg, cplx_t* out, size_t cap,
                        size_t* out_len) {
     if (insts_.empty()) return qdc_errf("The circuit is empty.");
-    if (!state_ || plan_.steps.empty()) return qdc_errf("backward() called before forward().");
+    // The reverse pass un-computes the state forward() left behind, replaying ITS plan: valid once per
+    // forward() of the unchanged program (src/circuit.rs:266-429 consumes self.state the same way).
+    if (!state_ || plan_.steps.empty() || !forward_valid_ || plan_key_.empty() || plan_key_[0] != (long)insts_.size())
+      return qdc_errf("backward() must follow a forward() of the same program (once per forward).");
+    forward_valid_ = false;
     stats_ = Stats();
     prof_.reset();
     std::vector<const cplx_t*> gp;

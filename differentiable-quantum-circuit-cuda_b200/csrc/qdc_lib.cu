@@ -137,8 +137,6 @@ QDC_EXPORT const char* qdc_circuit_set_option(qdc_circuit* c, const char* key, l
   else if (strcmp(key, "batch_dens") == 0) c->impl.opt_batch_dens_ = (int)value;  // 0: one sweep per density / seed
   else if (strcmp(key, "soa") == 0) c->impl.opt_soa_ = (int)value;    // f32 tile kernels: 0 selects the interleaved-layout kernels
   else if (strcmp(key, "peer") == 0) c->impl.opt_peer_ = (int)value;  // 0: force the NCCL send/recv exchange
-  else if (strcmp(key, "stagger") == 0) g_tile_stagger = (int)value;  // percent of the default CTA start skew (0: off)
-  else if (strcmp(key, "tile_debug") == 0) g_tile_debug = (int)value;  // profiling aid, results invalid when != 0
   else if (strcmp(key, "max_tile_gates") == 0) {
     if (value < 1 || value > QDC_TILE_MAXG_B) return qdc_errf("max_tile_gates must be in 1..%d.", QDC_TILE_MAXG_B);
     c->impl.opt_max_tile_gates_ = (int)value;
@@ -212,6 +210,7 @@ QDC_EXPORT const char* qdc_schedule(size_t n, size_t n_loc, int tile_bits, int l
   if (g_schedule_tile_strategy >= 0) so.tile_strategy = g_schedule_tile_strategy;
   qdc::Scheduler sch(si, so);
   const qdc::Plan plan = sch.run();
+  if (!plan.ok) return qdc_errf("the program cannot be scheduled on %zu local qubits per rank.", n_loc);
   std::vector<int64_t> enc;
   for (const qdc::Step& st : plan.steps) {
     const int64_t rec[8] = {st.type, st.inst, st.p2, st.p1, st.gbit, st.lpos, st.count, st.tb_count};

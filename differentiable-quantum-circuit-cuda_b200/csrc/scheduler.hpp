@@ -57,6 +57,7 @@ struct Plan {
   std::vector<int> tile_bits;
   std::vector<Group> groups;
   std::vector<int> final_map;     // logical qubit -> physical position after the plan
+  bool ok = true;                 // false: some instructions could not be scheduled (plan is truncated)
 };
 
 struct SchedInst {
@@ -110,7 +111,10 @@ class Scheduler {
         continue;
       }
       // nothing runnable: bring needed global qubits onto local positions
-      if (!remap(plan)) break;  // cannot happen for valid input; avoids an endless loop
+      if (!remap(plan)) {  // e.g. a dense two-qubit gate with a single local position: never placeable
+        plan.ok = false;
+        break;
+      }
     }
     plan.final_map = map_;
     return plan;

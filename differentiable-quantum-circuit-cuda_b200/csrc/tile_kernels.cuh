@@ -18,13 +18,12 @@
 // Once a pass holds more than ~4 gates the kernel leaves the HBM-bound regime
 // and becomes FP32/FP64-pipe bound (16 FMA per amplitude per 2-qubit gate).
 #pragma once
+#include <mutex>
+
 #include "circuit.cuh"
 
 #define QDC_TILE_NT_F 128  // threads per CTA, forward tile kernel (6 CTAs / SM: more independent barrier domains)
 #define QDC_TILE_NT_B 128  // backward tile kernel: fewer threads, more registers each (3 CTAs / SM)
-// default start skew between the CTA waves of an SM, per gate of the pass (~ tile time / resident CTAs)
-#define QDC_STAGGER_NS_PER_GATE_F 800
-#define QDC_STAGGER_NS_PER_GATE_B 1500
 
 #ifdef QDC_F64
 #define QDC_TILE_MAXG_F 48
@@ -66,11 +65,6 @@ struct TileGeo {
   BitDeposit hi;    // run index within the tile (T-L bits) -> amplitude offset
   BitDeposit tile;  // tile number (n-T bits)               -> amplitude base
   uint64_t ntiles;
-  int debug;  // profiling aid: 1 = skip HBM traffic, 2 = skip the gates (results are then wrong)
-  // De-phasing of the CTAs that share an SM (pair-lane kernels): the k-th of the `resident` CTAs of an SM
-  // starts k * stagger_ns late, so that the SM's CTAs do not fill / drain their tiles in lock-step (convoy:
-  // every CTA of the GPU loading at once is an HBM burst followed by an idle bus while all compute).
-  int nsm, resident, stagger_ns;
 };
 
 enum { TG_Q1 = 0, TG_Q2 = 1, TG_DIAG = 2 };
@@ -335,9 +329,9 @@ __global__ void __launch_bounds__(QDC_TILE_NT_F, 6)
   ta.init(p.geo);
   for (uint64_t tile = blockIdx.x; tile < p.geo.ntiles; tile += gridDim.x) {
     const uint64_t tbase = p.geo.tile(tile) >> QDC_LV;
-    if (p.geo.debug != 1) tile_io<QDC_TILE_NT_F, true>((vec_t*)state, smv, ta, tbase);
+    tile_io<QDC_TILE_NT_F, true>((vec_t*)state, smv, ta, tbase);
     __syncthreads();
-    for (int g = 0; g < (p.geo.debug == 2 ? 0 : p.ngates); g++) {
+    for (int g = 0; g < p.ngates; g++) {
       const TileGateF& G = p.g[g];
       if (G.type == TG_Q2) {
 #ifndef QDC_F64
@@ -375,7 +369,7 @@ __global__ void __launch_bounds__(QDC_TILE_NT_F, 6)
       }
       __syncthreads();
     }
-    if (p.geo.debug != 1) tile_io<QDC_TILE_NT_F, false>((vec_t*)state, smv, ta, tbase);
+    tile_io<QDC_TILE_NT_F, false>((vec_t*)state, smv, ta, tbase);
     __syncthreads();
   }
 }
@@ -471,12 +465,10 @@ __global__ void __launch_bounds__(QDC_TILE_NT_B, 3)
   ta.init(p.geo);
   for (uint64_t tile = blockIdx.x; tile < p.geo.ntiles; tile += gridDim.x) {
     const uint64_t tbase = p.geo.tile(tile) >> QDC_LV;
-    if (p.geo.debug != 1) {
-      tile_io<QDC_TILE_NT_B, true>((vec_t*)fwd, smf, ta, tbase);
-      tile_io<QDC_TILE_NT_B, true>((vec_t*)bwd, smb, ta, tbase);
-    }
+    tile_io<QDC_TILE_NT_B, true>((vec_t*)fwd, smf, ta, tbase);
+    tile_io<QDC_TILE_NT_B, true>((vec_t*)bwd, smb, ta, tbase);
     __syncthreads();
-    for (int g = 0; g < (p.geo.debug == 2 ? 0 : p.ngates); g++) {
+    for (int g = 0; g < p.ngates; g++) {
       const TileGateB& G = p.g[g];
       real_t acc[32];
 #pragma unroll
@@ -529,10 +521,8 @@ __global__ void __launch_bounds__(QDC_TILE_NT_B, 3)
         sm_acc[g * 32 + lane] += s;
       }
     }
-    if (p.geo.debug != 1) {
-      tile_io<QDC_TILE_NT_B, false>((vec_t*)fwd, smf, ta, tbase);
-      tile_io<QDC_TILE_NT_B, false>((vec_t*)bwd, smb, ta, tbase);
-    }
+    tile_io<QDC_TILE_NT_B, false>((vec_t*)fwd, smf, ta, tbase);
+    tile_io<QDC_TILE_NT_B, false>((vec_t*)bwd, smb, ta, tbase);
     __syncthreads();
   }
   for (int i = threadIdx.x; i < p.ngates * 32; i += QDC_TILE_NT_B)
@@ -567,9 +557,6 @@ __global__ void __launch_bounds__(QDC_TILE_NT_B, 3)
 #define QDC_KFWD k_tile_fwd
 #define QDC_KBWD k_tile_bwd
 #endif
-static int g_tile_debug = 0;
-static int g_tile_stagger = 0;  // option "stagger": percent of the default start skew per gate of the pass.
-                                // Off by default: measured no gain (28 q: 558.2 vs 558.2 ms/step at 0 / 100 %), i.e. no convoy.
 static inline const char* make_tile_geo_bits(std::vector<int> bits, int n_loc, int low_bits, TileGeo* geo,
                                              std::vector<int>* tile_pos_of);
 static inline const char* make_tile_geo(const qdc::Plan& plan, const qdc::Step& t, int n_loc, int low_bits,
@@ -582,14 +569,6 @@ static inline const char* make_tile_geo(const qdc::Plan& plan, const qdc::Step& 
 // Geometry of a tile over the physical positions `bits` (padded with the lowest unused positions).
 static inline const char* make_tile_geo_bits(std::vector<int> bits, int n_loc, int low_bits, TileGeo* geo,
                                              std::vector<int>* tile_pos_of) {
-  geo->debug = g_tile_debug;
-  geo->stagger_ns = 0;
-  geo->resident = 1;
-  {
-    DeviceInfo di;
-    QDC_TRY(qdc_device_info(&di));
-    geo->nsm = di.sm_count;
-  }
   // pad with the lowest unused positions so that T >= log2(threads * vector) and runs stay whole
   int T = (int)bits.size();
   // every thread gets at least one 4-vector quad item (QDC_LV + 10), and the register-blocked kernels need one
@@ -637,8 +616,11 @@ static inline const char* tile_grid(const void* kernel, int threads, size_t smem
   QDC_TRY(qdc_device_info(&di));
   // resident CTAs per SM of (kernel, threads, smem) on this device: queried once (the attribute call and the
   // occupancy query cost more than the launch itself on small registers)
+  // The attribute is per kernel and device for the whole PROCESS: the bookkeeping is process-wide too.
   struct Entry { const void* kernel; int threads, device; size_t smem; int bps; };
-  static thread_local std::vector<Entry> cache;
+  static std::vector<Entry> cache;
+  static std::mutex cache_mutex;
+  std::lock_guard<std::mutex> lock(cache_mutex);
   int bps = -1;
   for (const Entry& e : cache)
     if (e.kernel == kernel && e.threads == threads && e.smem == smem && e.device == di.device) bps = e.bps;
@@ -711,8 +693,6 @@ inline const char* Circuit::run_tile_forward(const qdc::Step& t, const std::vect
   const size_t smem = sizeof(cplx_t) << p.geo.T;
   int grid = 0;
   QDC_TRY(tile_grid((const void*)QDC_KFWD, QDC_TILE_NT_F, smem, p.geo.ntiles, &grid));
-  p.geo.resident = (grid + p.geo.nsm - 1) / p.geo.nsm;
-  p.geo.stagger_ns = g_tile_stagger * t.count * QDC_STAGGER_NS_PER_GATE_F / 100;
   cudaEvent_t pa = nullptr;
   if (prof_.on) pa = prof_.begin(stream_);
   QDC_KFWD<<<grid, QDC_TILE_NT_F, smem, stream_>>>(state_, p);
@@ -751,8 +731,6 @@ inline const char* Circuit::run_tile_backward(const qdc::Step& t, const std::vec
     const size_t smem = sizeof(cplx_t) << p.geo.T;
     int grid = 0;
     QDC_TRY(tile_grid((const void*)QDC_KFWD, QDC_TILE_NT_F, smem, p.geo.ntiles, &grid));
-    p.geo.resident = (grid + p.geo.nsm - 1) / p.geo.nsm;
-  p.geo.stagger_ns = g_tile_stagger * t.count * QDC_STAGGER_NS_PER_GATE_F / 100;
     cudaEvent_t pa = nullptr;
     if (prof_.on) pa = prof_.begin(stream_);
     QDC_KFWD<<<grid, QDC_TILE_NT_F, smem, stream_>>>(state_, p);
@@ -793,8 +771,6 @@ inline const char* Circuit::run_tile_backward(const qdc::Step& t, const std::vec
                       2 * (QDC_TILE_NT_B / 32) * 32 * sizeof(real_t);
   int grid = 0;
   QDC_TRY(tile_grid((const void*)QDC_KBWD, QDC_TILE_NT_B, smem, p.geo.ntiles, &grid));
-  p.geo.resident = (grid + p.geo.nsm - 1) / p.geo.nsm;
-  p.geo.stagger_ns = g_tile_stagger * t.count * QDC_STAGGER_NS_PER_GATE_B / 100;
   const size_t need = (size_t)grid * QDC_TILE_MAXG_B * 32;
   if (need > tile_partials_cap_) {
     if (tile_partials_) QDC_CUDA(cudaFree(tile_partials_));

@@ -116,50 +116,6 @@ __device__ __forceinline__ void tile_io_soa(vec_t* __restrict__ gmem, vec_t* __r
   }
 }
 
-// L2 prefetch of a tile this CTA will load later (its next tile): one
-// `prefetch.global.L2` per 128-byte line, issued by the thread that will load the
-// line's first vector.  Costs no registers or shared memory (a double-buffered
-// smem prefetch would halve the resident CTAs); the later fill then pays L2
-// latency instead of HBM latency.  ncu (profiles/r1_tile_bwd_soa_28q_ncu.txt):
-// 36 % of the reverse kernel's warp samples sat in the per-tile fill / drain code --
-// but that wait is hidden behind the SM's other CTAs: measured gain 0.5 % (28 q, depth
-// 40: 558.9 -> 555.7 ms/step), so the prefetch is compiled out by default.
-#ifndef QDC_TILE_PREFETCH
-#define QDC_TILE_PREFETCH 0
-#endif
-template <int NT>
-__device__ __forceinline__ void tile_prefetch_l2(const vec_t* __restrict__ gmem, const TileAddr<NT>& ta,
-                                                 uint64_t tile_base_vec) {
-#if QDC_TILE_PREFETCH
-  if ((threadIdx.x & 7) == 0) {  // 8 vectors = 128 bytes; runs are >= 128-byte aligned
-    const vec_t* p = gmem + tile_base_vec + ta.lo;
-#pragma unroll
-    for (int i = 0; i < TileAddr<NT>::MAXI; i++)
-      if (i < ta.niter) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + ((uint64_t)ta.it[i] << ta.runv_log)));
-  }
-#endif
-}
-
-// start skew of the CTAs sharing an SM (see TileGeo::stagger_ns): the k-th CTA to arrive on an SM
-// (arrival counter per %smid, never reset: only the order modulo the resident CTAs matters) starts
-// (k mod resident) * stagger_ns late.
-__device__ unsigned g_sm_arrivals[1024];
-__device__ __forceinline__ void tile_stagger(const TileGeo& geo) {
-  if (geo.stagger_ns > 0) {
-    if (threadIdx.x == 0) {
-      unsigned smid;
-      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-      const unsigned k = atomicAdd(&g_sm_arrivals[smid & 1023u], 1u) % (unsigned)geo.resident;
-      for (unsigned left = k * (unsigned)geo.stagger_ns; left > 0;) {
-        const unsigned d = left > 500000u ? 500000u : left;
-        __nanosleep(d);
-        left -= d;
-      }
-    }
-    __syncthreads();
-  }
-}
-
 // ---------------------------------------------------------------- forward
 template <int NT, class Geo>
 __device__ __forceinline__ void tile_apply_soa(vec_t* smv, const Geo& geo, int nitems, const GateMat& G) {
@@ -262,14 +218,11 @@ __global__ void __launch_bounds__(QDC_TILE_NT_F, 6)
   const int nvec = 1 << (p.geo.T - QDC_LV);
   TileAddr<QDC_TILE_NT_F> ta;
   ta.init(p.geo);
-  tile_stagger(p.geo);
   for (uint64_t tile = blockIdx.x; tile < p.geo.ntiles; tile += gridDim.x) {
     const uint64_t tbase = p.geo.tile(tile) >> QDC_LV;
-    if (p.geo.debug != 1) tile_io_soa<QDC_TILE_NT_F, true>((vec_t*)state, smv, ta, tbase);
-    if (tile + gridDim.x < p.geo.ntiles && p.geo.debug != 1)
-      tile_prefetch_l2<QDC_TILE_NT_F>((const vec_t*)state, ta, p.geo.tile(tile + gridDim.x) >> QDC_LV);
+    tile_io_soa<QDC_TILE_NT_F, true>((vec_t*)state, smv, ta, tbase);
     __syncthreads();
-    for (int g = 0; g < (p.geo.debug == 2 ? 0 : p.ngates); g++) {
+    for (int g = 0; g < p.ngates; g++) {
       const TileGateF& G = p.g[g];
       if (G.type == TG_Q2) {
         if (G.b == 0) {
@@ -298,7 +251,7 @@ __global__ void __launch_bounds__(QDC_TILE_NT_F, 6)
       }
       __syncthreads();
     }
-    if (p.geo.debug != 1) tile_io_soa<QDC_TILE_NT_F, false>((vec_t*)state, smv, ta, tbase);
+    tile_io_soa<QDC_TILE_NT_F, false>((vec_t*)state, smv, ta, tbase);
     __syncthreads();
   }
 }
@@ -440,20 +393,12 @@ __global__ void __launch_bounds__(QDC_TILE_NT_B, 3)
   __syncthreads();
   TileAddr<QDC_TILE_NT_B> ta;
   ta.init(p.geo);
-  tile_stagger(p.geo);
   for (uint64_t tile = blockIdx.x; tile < p.geo.ntiles; tile += gridDim.x) {
     const uint64_t tbase = p.geo.tile(tile) >> QDC_LV;
-    if (p.geo.debug != 1) {
-      tile_io_soa<QDC_TILE_NT_B, true>((vec_t*)fwd, smf, ta, tbase);
-      tile_io_soa<QDC_TILE_NT_B, true>((vec_t*)bwd, smb, ta, tbase);
-      if (tile + gridDim.x < p.geo.ntiles) {
-        const uint64_t nbase = p.geo.tile(tile + gridDim.x) >> QDC_LV;
-        tile_prefetch_l2<QDC_TILE_NT_B>((const vec_t*)fwd, ta, nbase);
-        tile_prefetch_l2<QDC_TILE_NT_B>((const vec_t*)bwd, ta, nbase);
-      }
-    }
+    tile_io_soa<QDC_TILE_NT_B, true>((vec_t*)fwd, smf, ta, tbase);
+    tile_io_soa<QDC_TILE_NT_B, true>((vec_t*)bwd, smb, ta, tbase);
     __syncthreads();
-    for (int g = 0; g < (p.geo.debug == 2 ? 0 : p.ngates); g++) {
+    for (int g = 0; g < p.ngates; g++) {
       const TileGateB& G = p.g[g];
       real_t acc[32];
 #pragma unroll
@@ -484,20 +429,11 @@ __global__ void __launch_bounds__(QDC_TILE_NT_B, 3)
         tile_rev_diag_soa_hh<QDC_TILE_NT_B>(smf, smb, geo, nvec / 4, G, acc);
       }
       real_t* part = sm_part + (size_t)(g & 1) * NW * 32;
-#ifdef QDC_EXPERIMENT_NO_FLUSH  // timing experiment only (gradients wrong): cost of the per-gate reduction
-      if (G.slot >= 0) {
-        real_t t = 0;
-#pragma unroll
-        for (int k = 0; k < 32; k++) t += acc[k];
-        if (t == 12345.f) part[warp * 32 + lane] = t;
-      }
-#else
       if (G.slot >= 0) {
         double d = 0.0;
         warp_flush<32>(acc, d, lane);  // lane j now holds the warp total of value j
         part[warp * 32 + lane] = (real_t)d;
       }
-#endif
       __syncthreads();
       if (G.slot >= 0 && warp == 0) {
         double s = 0.0;
@@ -506,10 +442,8 @@ __global__ void __launch_bounds__(QDC_TILE_NT_B, 3)
         sm_acc[g * 32 + lane] += s;
       }
     }
-    if (p.geo.debug != 1) {
-      tile_io_soa<QDC_TILE_NT_B, false>((vec_t*)fwd, smf, ta, tbase);
-      tile_io_soa<QDC_TILE_NT_B, false>((vec_t*)bwd, smb, ta, tbase);
-    }
+    tile_io_soa<QDC_TILE_NT_B, false>((vec_t*)fwd, smf, ta, tbase);
+    tile_io_soa<QDC_TILE_NT_B, false>((vec_t*)bwd, smb, ta, tbase);
     __syncthreads();
   }
   for (int i = threadIdx.x; i < p.ngates * 32; i += QDC_TILE_NT_B)

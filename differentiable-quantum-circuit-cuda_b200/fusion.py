@@ -200,14 +200,37 @@ class FusedCircuit(Circuit):
         if self._inner is not None and hasattr(self._inner, "set_option"):
             self._inner.set_option(key, int(value))
 
+    # statistics / state access / I/O act on the circuit that executes the fused program (built on demand)
     def last_stats(self):
-        return self._inner.last_stats()
+        return self._build().last_stats()
 
     def last_profile(self):
-        return self._inner.last_profile()
+        return self._build().last_profile()
 
     def get_cpu_state_copy(self):
-        return self._inner.get_cpu_state_copy()
+        return self._build().get_cpu_state_copy()
+
+    def save_state(self, path: str):
+        return self._build().save_state(path)
+
+    def load_state(self, path: str):
+        return self._build().load_state(path)
+
+    def state_layout(self):
+        return self._build().state_layout()
+
+    def set_stream(self, cuda_stream):
+        return self._build().set_stream(cuda_stream)
+
+    def _count(self, what):
+        """Counts of the USER's program (not of the fused one), like Circuit._count."""
+        dens_len = lambda k: 4 if k in (Q1_DENS, DIFF_Q1_DENS) else 16            # noqa: E731
+        gate_len = lambda k: 16 if k in (CONST_Q2, VAR_Q2, CONST_Q2_NONU, VAR_Q2_NONU) else 4   # noqa: E731
+        ks = self._kinds
+        diff = (DIFF_Q1_DENS, DIFF_Q2_DENS)
+        return [len(ks), sum(k not in _DENS and k not in _VAR for k in ks), sum(k in _VAR for k in ks),
+                sum(k in _DENS for k in ks), sum(k in diff for k in ks), sum(dens_len(k) for k in ks if k in _DENS),
+                sum(dens_len(k) for k in ks if k in diff), sum(gate_len(k) for k in ks if k in _VAR)][what]
 
     @property
     def fused_gate_count(self) -> int:
@@ -267,9 +290,12 @@ class FusedCircuit(Circuit):
             raise ValueError("The number of constant gates does not match the circuit.")
         if len(var_gates) != self._n_var:
             raise ValueError("The number of variable gates does not match the circuit.")
-        lists = ([np.asarray(g, dtype=dt).reshape(-1) for g in const_gates],
-                 [np.asarray(g, dtype=dt).reshape(-1) for g in var_gates])
-        return lists
+        def strict(g):   # same strictness as Circuit (PyO3's PyReadonlyArray1<Complex>): no silent dtype casts
+            g = np.asarray(g)
+            if g.dtype != dt:
+                raise TypeError(f"gate arrays must have dtype {dt}, got {g.dtype}")
+            return g.reshape(-1)
+        return [strict(g) for g in const_gates], [strict(g) for g in var_gates]
 
     def _fuse(self, const_gates, var_gates):
         """-> (inner const list, inner var list, per-batch member stacks for the chain rule)"""

@@ -209,6 +209,15 @@ class RefCircuit(oc.OracleCircuit):
         self.instructions = []
         self.state_t = RefTensor.new_standard(self.lib, qubits_number)  # src/circuit.rs:96
         self.initial_t = self.state_t.clone()                           # :100
+        # Optional timing hook of bench.py --impl reference: called with "gates" / "densities" whenever the
+        # replay moves from gate instructions to density instructions or back (the caller records an event).
+        self.on_phase = None
+        self._phase = None
+
+    def _enter(self, phase):
+        if self.on_phase is not None and phase != self._phase:
+            self.on_phase(phase)
+        self._phase = phase
 
     def set_state_from_vector(self, vector):
         self.initial_t.set_from_host(vector)
@@ -217,10 +226,13 @@ class RefCircuit(oc.OracleCircuit):
         assert self.instructions, "The circuit is empty."
         out = []
         cq, vq = deque(const_gates), deque(var_gates)
+        self._phase = None
+        self._enter("gates")
         self.lib.call("copy", self.initial_t.ptr, self.state_t.ptr, self.n)  # data_transfer
         st = self.state_t
         for inst in self.instructions:
             k = inst[0]
+            self._enter("gates" if k in oc._Q1_GATES or k in oc._Q2_GATES or k in oc._DIAG_GATES else "densities")
             if k in oc._Q1_GATES:
                 st.apply_q1_gate((vq if k in oc._VAR else cq).popleft(), inst[1])
             elif k in oc._Q2_GATES:
@@ -241,10 +253,12 @@ class RefCircuit(oc.OracleCircuit):
         fwd, bwd = self.state_t, None
         grads = deque()
         z = lambda m: np.zeros(m, dtype=self.dtype)  # noqa: E731
+        self._phase = None
         for inst in reversed(self.instructions):
             k = inst[0]
             if k in (oc.Q1_DENS, oc.Q2_DENS):
                 continue
+            self._enter("densities" if k in (oc.DIFF_Q1_DENS, oc.DIFF_Q2_DENS) else "gates")
             if k in (oc.DIFF_Q1_DENS, oc.DIFF_Q2_DENS):
                 g = gd.pop()
                 add = fwd.conj_and_double()

@@ -37,10 +37,22 @@ def test_library_loads_and_exports_every_declared_symbol(pkg, precision):
     for name in declared_symbols():
         assert hasattr(lib.cdll, name), f"{name} declared in include/ but not exported by {lib.path}"
     out = subprocess.run(["nm", "-D", "--defined-only", lib.path], capture_output=True, text=True).stdout
-    exported = {line.split()[-1] for line in out.splitlines() if " T " in line}
+    # every defined dynamic symbol whatever its type (T, W weak template instantiations, V, D, B ...)
+    exported = {line.split()[-1] for line in out.splitlines() if len(line.split()) >= 3}
     assert set(declared_symbols()) <= exported
-    # nothing but the ABI leaks out of the library
-    assert all(not s.startswith("_Z") for s in exported), "C++ symbols are exported"
+    # nothing but the ABI leaks out of the library (csrc/qdc_exports.map)
+    leaked = sorted(exported - set(declared_symbols()))
+    assert leaked == [], f"symbols outside include/*.h are exported: {leaked[:8]}"
+
+
+@pytest.mark.parametrize("precision", ["f32", "f64"])
+def test_library_does_not_embed_the_static_cuda_runtime(pkg, precision):
+    """Built with -cudart shared: the library names only the runtime entry points it calls."""
+    out = subprocess.run(["nm", "-D", "--undefined-only", pkg.lib_path(precision)], capture_output=True,
+                         text=True).stdout
+    assert "cudaLaunchKernel" in out
+    blob = open(pkg.lib_path(precision), "rb").read()
+    assert b"MemcpyBatch" not in blob
 
 
 def test_python_binding_covers_every_declared_symbol(pkg):

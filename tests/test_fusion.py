@@ -125,7 +125,7 @@ def test_fused_circuit_on_the_gpu_matches_the_oracle(precision):
         _build(case, f, n)
         dens_o = o.forward(const, var)
         dens_f = f.forward(const, var)
-        tol = 1e-4 if precision == "f32" else 1e-11
+        tol = 1e-5 if precision == "f32" else 1e-12
         for a, b in zip(dens_f, dens_o):
             assert np.abs(a - b).max() < tol
         _, cts = tsallis_loss_and_cotangents(dens_o)
