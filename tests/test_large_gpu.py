@@ -97,7 +97,14 @@ def test_default_tiles_match_the_unmodified_reference_at_30q(pkg, precision):
 
 
 def test_default_tiles_match_reference_and_per_gate_executor_at_32q(pkg):
-    """The benchmark's register: 2^32 amplitudes, tile bases beyond 32 bits."""
+    """The benchmark's register: 2^32 amplitudes, tile bases beyond 32 bits.
+
+    At this size the REFERENCE's own f32 gradient reduction is the least accurate party: every thread of its
+    <<<128,128>>> launch adds 2^31 / 16384 = 131072 products sequentially in f32 (src/primitives.cu:222-247).
+    Measured on B200: tiled vs per-gate executor 1.7e-7, either of them vs the reference 4.2e-5.  The f64
+    build (pinned to the reference's f64 build at 1e-15 by the 30 q test above) is therefore the arbiter:
+    this library must be within 1e-5 of it, and its distance to the reference must be explained by the
+    reference's own distance to the arbiter."""
     n, depth = 32, 2
     if _free_gib() < 4 * 32 + 4:
         pytest.skip("needs 132 GiB of free device memory")
@@ -107,12 +114,19 @@ def test_default_tiles_match_reference_and_per_gate_executor_at_32q(pkg):
     e0d, e0g = _max_rel(dens, dens0), _max_rel(grads, grads0)
     rec = {"precision": "f32", "depth": depth, "err_density_vs_per_gate": e0d, "err_gradient_vs_per_gate": e0g}
     assert abs(float(np.trace(dens[0]).real) - 1.0) < 1e-5
+    (dens64, grads64), _ = _ours(n, depth, "f64")                    # arbiter (2 x 64 GiB)
+    rec["err_density_vs_f64"] = _max_rel(dens, dens64)
+    rec["err_gradient_vs_f64"] = _max_rel(grads, grads64)
     if rr.ref_available("f32", big=True):
         dens_r, grads_r = _reference(n, depth, "f32")
         rec["err_density_vs_reference"] = _max_rel(dens, dens_r)
         rec["err_gradient_vs_reference"] = _max_rel(grads, grads_r)
-        rec["per_gate_err_gradient_vs_reference"] = _max_rel(grads0, grads_r)
+        rec["reference_err_density_vs_f64"] = _max_rel(dens_r, dens64)
+        rec["reference_err_gradient_vs_f64"] = _max_rel(grads_r, grads64)
     _record("32q", rec)
     assert e0d < 1e-5 and e0g < 1e-5, rec
+    assert rec["err_density_vs_f64"] < 1e-5 and rec["err_gradient_vs_f64"] < 1e-5, rec
     if "err_density_vs_reference" in rec:
-        assert rec["err_density_vs_reference"] < 1e-5 and rec["err_gradient_vs_reference"] < 1e-5, rec
+        # |ours - ref| <= |ours - exact| + |ref - exact|: nothing beyond the reference's own rounding error
+        assert rec["err_density_vs_reference"] < 1e-5 + rec["reference_err_density_vs_f64"], rec
+        assert rec["err_gradient_vs_reference"] < 1e-5 + rec["reference_err_gradient_vs_f64"], rec
