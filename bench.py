@@ -295,6 +295,8 @@ def make_circuit(args, world, n_total, precision, workload, depth, opts=None):
         o["peer"] = args.peer
     if precision == "f32":
         o["soa"] = args.soa
+    if precision == "f32" and args.tc >= 0:
+        o["tc"] = args.tc
     for key, val in (("rb_policy", args.rb_policy), ("batch_dens", args.batch_dens),
                      ("tile_strategy", args.tile_strategy)):
         if val >= 0:
@@ -418,6 +420,31 @@ def roofline_block(prof, dev_ms, steps, precision, local_qubits, kinds, clocks):
         r["dram_gbs"] = round(passes * S * e["launches"] / sec / 1e9, 1)
         r["dram_frac"] = round(r["dram_gbs"] / peak, 4)
         r["gates_per_launch"] = round(r["algorithmic_bytes_per_launch"] / float(passes * S), 2)
+    if name in ("tc_bwd", "tc_fwd"):
+        # tensor-core fused blocks (csrc/tc_block.cuh): one 64 x 64 block per HBM sweep.  Reverse step of a block =
+        # un-compute (2*S) + block gradient (2*S read) + adjoint pull-back (2*S) = 6*S of real traffic.
+        passes = 6 if name == "tc_bwd" else 2
+        alg = 4 if name == "tc_bwd" else 2
+        tiles = float(1 << (local_qubits - 12))
+        mma_flop = 2.0 * 128 * 64 * 16                     # one tcgen05.mma of the block kernel (M 128, N 64, K 16)
+        per_tile = (2 * 64 + 24 * 2) * mma_flop if name == "tc_bwd" else 64 * mma_flop
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:  # noqa: BLE001
+            pass
+        tpeak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0)))
+        r["bound"] = "hbm"
+        r["traffic"] = passes * S
+        r["traffic_source"] = "= %d*S per block (state and adjoint read + written once per kernel of the block)" % passes
+        r["dram_gbs"] = round(passes * S * e["launches"] / sec / 1e9, 1)
+        r["dram_frac"] = round(r["dram_gbs"] / peak, 4)
+        r["tensor_tflops"] = round(per_tile * tiles * e["launches"] / sec / 1e12, 1)
+        r["tensor_peak_tflops"] = tpeak
+        r["tensor_frac"] = round(r["tensor_tflops"] / tpeak, 4)
+        r["tensor_note"] = ("bf16 tcgen05.mma on exact 9 / 8-bit slices of the f32 data, 64 (48 + 16) + 24 x 2 instructions "
+                            "of 128 x 64 x 16 per 2^12-amplitude tile; peak = measured cuBLAS bf16 (sustained)")
+        r["gates_per_launch"] = round(r["algorithmic_bytes_per_launch"] / float(alg * S), 2)
     return r
 
 
@@ -474,7 +501,9 @@ def run_workload(args, world, rank, local, precision, workload, local_qubits, de
                    "gate_fusion": bool(args.fusion and world == 1),
                    "executor": ["one pass per gate", "tiled multi-gate passes",
                                 "tiled multi-gate passes, forward kernel (register-blocked or per gate) by gate mix"][args.fuse]
-                               + (", pair-lane smem layout" if precision == "f32" and args.soa and args.fuse else "")},
+                               + (", pair-lane smem layout" if precision == "f32" and args.soa and args.fuse else "")
+                               + (", tensor-core fused 6-qubit blocks (tcgen05, exact bf16 slices)"
+                                  if "tc_fwd" in prof or "tc_bwd" in prof else "")},
         "effective_hbm_gbs": round(total_alg * world / (dev_ms * 1e-3) / 1e9, 1),
         "effective_hbm_frac": round(total_alg / (dev_ms * 1e-3) / 1e9 / peak, 4),
         "roofline": roofline_block(prof, dev_ms, steps, precision, local_qubits, kinds, clocks),
@@ -626,6 +655,7 @@ def main():
     ap.add_argument("--rb-policy", type=int, default=-1, help="fuse=2 forward: 0 never register-block, 1 always, 2 by gate mix (default)")
     ap.add_argument("--batch-dens", type=int, default=-1, help="0: one sweep per density / seed")
     ap.add_argument("--tile-strategy", type=int, default=-1, help="scheduler tiling: 2 window growth with look-ahead (default), 1 window growth, 0 first-fit")
+    ap.add_argument("--tc", type=int, default=-1, help="f32: 1 tensor-core fused 6-qubit blocks, 0 FP32-pipe tile kernels only (-1: library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-check", action="store_true", help="skip the parity check that precedes the timed steps")
     ap.add_argument("--secondary", type=int, default=1,

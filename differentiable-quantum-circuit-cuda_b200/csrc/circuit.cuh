@@ -19,6 +19,9 @@
 #include "engine.cuh"
 #include "nccl_dyn.hpp"
 #include "scheduler.hpp"
+#ifndef QDC_F64
+#include "tc_block.cuh"
+#endif
 
 enum Kind {
   K_CONST_Q2 = 0, K_VAR_Q2, K_CONST_Q2_NONU, K_VAR_Q2_NONU, K_CONST_Q2_DIAG, K_VAR_Q2_DIAG,
@@ -53,6 +56,8 @@ struct Stats {
 
 struct DensGroup;
 struct TileDensParams;
+struct TcState;
+struct TcPass;
 
 struct GateList {
   const cplx_t* flat;
@@ -64,11 +69,11 @@ struct GateList {
 // (enabled by option "profile"); feeds bench.py's roofline block.
 enum ProfCat {
   CAT_FWD_Q1 = 0, CAT_FWD_Q2, CAT_FWD_DIAG, CAT_DENSITY, CAT_SEED, CAT_UNCOMPUTE, CAT_REV_Q1, CAT_REV_Q2,
-  CAT_REV_DIAG, CAT_REV_CONST, CAT_TILE_FWD, CAT_TILE_BWD, CAT_EXCHANGE, CAT_COUNT
+  CAT_REV_DIAG, CAT_REV_CONST, CAT_TILE_FWD, CAT_TILE_BWD, CAT_EXCHANGE, CAT_TC_FWD, CAT_TC_BWD, CAT_COUNT
 };
 static const char* const kProfCatNames[CAT_COUNT] = {
     "fwd_q1", "fwd_q2", "fwd_diag", "density", "seed", "uncompute", "rev_q1", "rev_q2",
-    "rev_diag", "rev_const", "tile_fwd", "tile_bwd", "exchange"};
+    "rev_diag", "rev_const", "tile_fwd", "tile_bwd", "exchange", "tc_fwd", "tc_bwd"};
 
 struct ProfEntry {
   uint64_t launches = 0;
@@ -215,6 +220,11 @@ class Circuit {
   int opt_tile_strategy_ = 2;  // scheduler.hpp: 2 window growth with look-ahead, 1 window growth, 0 first-fit tiling
   int opt_batch_dens_ = 1;    // 1: densities / density seeds of one program point share tiled sweeps (tile_dens_kernels.cuh)
   int opt_soa_ = 1;           // f32 tile kernels: 1 pair-lane shared-memory layout (tile_soa_kernels.cuh), 0 interleaved
+  // f32: 1 = windows of <= 6 qubits on positions >= 3 run as dense 64 x 64 blocks on the tensor cores
+  // (tc_exec.cuh / tc_block.cuh); the scheduler then grows 6-position windows
+  int opt_tc_ = 0;
+  int opt_tc_products_ = 8;   // bf16 slice products per block (tc_block.cuh)
+  TcState* tc_ = nullptr;
   int opt_tile_bits_ = 0;  // 0: default for the precision
   int opt_low_bits_ = 0;
 #ifdef QDC_F64
@@ -241,6 +251,9 @@ class Circuit {
     d_res_slots_ = 0;
     ws_release(ws_);
     release_tiles();
+#ifndef QDC_F64
+    release_tc();
+#endif
     for (int r = 0; r < kMaxWorld; r++) {
       if (peer_state_[r]) cudaIpcCloseMemHandle(peer_state_[r]);
       if (peer_bwd_[r]) cudaIpcCloseMemHandle(peer_bwd_[r]);
@@ -594,7 +607,25 @@ class Circuit {
 #endif
   }
 
+  bool tc_active() const {
+#ifndef QDC_F64
+    return opt_tc_ && opt_fuse_ && n_loc_ >= 14;
+#else
+    return false;
+#endif
+  }
+
+  // options of the gate scheduler: 6-position windows when the tensor-core blocks are on
   qdc::SchedOptions sched_options() const {
+    qdc::SchedOptions so = base_options();
+    if (tc_active() && so.tile_bits) {
+      so.tile_bits = 6;
+      so.low_bits = 0;
+    }
+    return so;
+  }
+
+  qdc::SchedOptions base_options() const {
     qdc::SchedOptions so;
     so.n = n_;
     so.n_loc = n_loc_;
@@ -616,7 +647,8 @@ class Circuit {
   void build_plan(bool all_dens) {
     const qdc::SchedOptions so = sched_options();
     const std::vector<long> key = {(long)insts_.size(), all_dens ? 1L : 0L, so.n, so.n_loc, so.tile_bits, so.low_bits,
-                                   so.max_tile_gates, so.min_tile_gates, so.group_bits, so.swap_min_pos, so.tile_strategy};
+                                   so.max_tile_gates, so.min_tile_gates, so.group_bits, so.swap_min_pos, so.tile_strategy,
+                                   tc_active() ? 1L : 0L};
     if (key == plan_key_ && !plan_.steps.empty()) return;
     plan_key_ = key;
     std::vector<qdc::SchedInst> si(insts_.size());
@@ -800,6 +832,9 @@ class Circuit {
                       "its qubits local).", n_loc_);
     QDC_TRY(reset_state());
     if (nslots) QDC_CUDA(cudaMemsetAsync(d_res_, 0, nslots * 32 * sizeof(double), stream_));
+#ifndef QDC_F64
+    QDC_TRY(tc_begin(false));
+#endif
     QDC_TRY(run_forward(gp, all_dens));
     cur_map_ = plan_.final_map;
     forward_valid_ = true;
@@ -871,6 +906,12 @@ class Circuit {
           QDC_TRY(fwd_gate_step(st, gp));
           break;
         case qdc::ST_TILE:
+#ifndef QDC_F64
+          if (tc_step_ok(st)) {
+            QDC_TRY(run_tc_forward(st, gp, false));
+            break;
+          }
+#endif
           if (opt_fuse_ >= 2) QDC_TRY(run_tile_forward_blocked(st, gp, false));
           else QDC_TRY(run_tile_forward(st, gp));
           break;
@@ -954,6 +995,9 @@ class Circuit {
       for (size_t i = 0; i < insts_.size(); i++)
         if (kind_is_gate(insts_[i].kind) && kind_is_var(insts_[i].kind)) vslot[i] = s++;
     }
+#ifndef QDC_F64
+    QDC_TRY(tc_begin(true));
+#endif
     QDC_TRY(run_backward(gp, dp, vslot));
     cur_map_.clear();  // every swap has been replayed in reverse: identity layout again
     if (nvar) {
@@ -962,10 +1006,23 @@ class Circuit {
     }
     QDC_CUDA(cudaStreamSynchronize(stream_));
     if (prof_.on) prof_.collect();
+#ifndef QDC_F64
+    QDC_TRY(tc_finish_backward());
+#endif
     size_t o = 0;
     for (size_t i = 0; i < insts_.size(); i++) {
       if (vslot[i] < 0) continue;
       const Inst& in = insts_[i];
+#ifndef QDC_F64
+      if (const std::vector<zc>* tg = tc_gradient(i)) {   // gate of a tensor-core block: already in reference order
+        for (size_t j = 0; j < tg->size(); j++) {
+          out[o + j].x = (real_t)(*tg)[j].real();
+          out[o + j].y = (real_t)(*tg)[j].imag();
+        }
+        o += tg->size();
+        continue;
+      }
+#endif
       const double* h = &h_res_[(size_t)vslot[i] * 32];
       if (kind_is_q2dense(in.kind)) {
         zc m[16];
@@ -1048,6 +1105,13 @@ class Circuit {
           QDC_TRY(bwd_gate_step(st, gp, vslot, live));
           break;
         case qdc::ST_TILE:
+#ifndef QDC_F64
+          if (tc_step_ok(st)) {
+            if (live) QDC_TRY(run_tc_backward(st, gp));
+            else QDC_TRY(run_tc_forward(st, gp, true));
+            break;
+          }
+#endif
           if (opt_fuse_ >= 2) {
             // The register-blocked reverse kernel (2 x 16 amplitudes + 32 accumulators per thread)
             // is occupancy-starved and measured slower than the per-gate tile kernel (fuse = 3
@@ -1104,6 +1168,19 @@ class Circuit {
     return uncompute ? run_tile_backward(t, gp, std::vector<long>(), false) : run_tile_forward(t, gp);
   }
   void release_tiles();
+#ifndef QDC_F64
+  // tensor-core fused blocks (tc_exec.cuh)
+  void release_tc();
+  bool tc_step_ok(const qdc::Step& t) const;
+  const char* tc_ensure(size_t image_slots, size_t grad_slots);
+  const char* tc_begin(bool backward);
+  const char* tc_prepare(const qdc::Step& t, const std::vector<const cplx_t*>& gp, tcb::Params* geo, TcPass* pass);
+  const char* tc_launch_block(cplx_t* buf, const tcb::Params& geo, const std::vector<zc>& w, int form);
+  const char* run_tc_forward(const qdc::Step& t, const std::vector<const cplx_t*>& gp, bool uncompute);
+  const char* run_tc_backward(const qdc::Step& t, const std::vector<const cplx_t*>& gp);
+  const char* tc_finish_backward();
+  const std::vector<zc>* tc_gradient(size_t inst) const;
+#endif
   // batched densities / seeds (tile_dens_kernels.cuh)
   const char* fill_dens_params(const DensGroup& g, TileDensParams* p, std::vector<int>* tpos);
   const char* run_dens_group(const DensGroup& g, const std::vector<long>& dslot);

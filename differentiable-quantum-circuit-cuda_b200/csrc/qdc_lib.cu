@@ -7,6 +7,7 @@
 #include "tile_soa_kernels.cuh"
 #include "tile_rb_soa_kernels.cuh"
 #include "tile_dens_kernels.cuh"
+#include "tc_exec.cuh"
 
 struct qdc_circuit {
   Circuit impl;
@@ -137,7 +138,15 @@ QDC_EXPORT const char* qdc_circuit_set_option(qdc_circuit* c, const char* key, l
   else if (strcmp(key, "batch_dens") == 0) c->impl.opt_batch_dens_ = (int)value;  // 0: one sweep per density / seed
   else if (strcmp(key, "soa") == 0) c->impl.opt_soa_ = (int)value;    // f32 tile kernels: 0 selects the interleaved-layout kernels
   else if (strcmp(key, "peer") == 0) c->impl.opt_peer_ = (int)value;  // 0: force the NCCL send/recv exchange
-  else if (strcmp(key, "max_tile_gates") == 0) {
+  else if (strcmp(key, "tc") == 0) {   // f32: tensor-core fused 6-qubit blocks (tc_exec.cuh)
+#ifdef QDC_F64
+    if (value) return qdc_errf("option \"tc\" exists in the f32 build only.");
+#endif
+    c->impl.opt_tc_ = (int)value;
+  } else if (strcmp(key, "tc_products") == 0) {
+    if (value != 6 && value != 8) return qdc_errf("tc_products must be 6 or 8.");
+    c->impl.opt_tc_products_ = (int)value;
+  } else if (strcmp(key, "max_tile_gates") == 0) {
     if (value < 1 || value > QDC_TILE_MAXG_B) return qdc_errf("max_tile_gates must be in 1..%d.", QDC_TILE_MAXG_B);
     c->impl.opt_max_tile_gates_ = (int)value;
   } else return qdc_errf("Unknown option \"%s\".", key);

@@ -14,6 +14,7 @@
 // grid g0 = 2^(E-7) (2^E > max |x| of the tile), into three BF16 numbers
 //
 //     x = p0 + p1 + p2 + r,   p_i = k_i * g0 * 2^(-8 i),  |k_i| <= 128,  |r| <= 2^(E-24)
+//     (forward kernel: 9 bits per slice, g0 = 2^(E-8), p_i = k_i * g0 * 2^(-9 i), |k_i| <= 256, |r| <= 2^(E-27))
 //
 // (three magic-number roundings, 8 FADD per value; the high 16 bits of each f32 slice ARE the bf16).
 // W is sliced the same way on the host (grid 2^-7).  The leading products p0(W) * p0(X) are integers
@@ -51,14 +52,19 @@ constexpr int kDim = 128;          // 2 * 2^6: real-ified block dimension (M and
 constexpr int kN = 64;             // rest columns per tile
 constexpr int kTileBits = 12;      // 2^12 amplitudes per tile
 constexpr int kSlices = 3;
-constexpr int kSliceBytesW = kDim * kDim * 2;          // 32 KiB per W slice
+constexpr int kSliceBytesW = kDim * kDim * 2;          // 32 KiB per W slice (global image; lives in TMEM in the kernel)
 constexpr int kSliceBytesX = kDim * kN * 2;            // 16 KiB per X slice
 constexpr int kStageBytes = kSlices * kSliceBytesX;    // 48 KiB per pipeline stage
-constexpr int kStages = 2;
-constexpr int kSmemW = kSlices * kSliceBytesW;         // 96 KiB
-constexpr int kSmemBytes = kSmemW + kStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
-constexpr int kThreads = 288;
-constexpr int kTmemCols = 256;     // 2 stages x (A0, A1) x 64 columns
+constexpr int kStages = 4;                             // shared-memory stages (fill may run 3 tiles ahead of the drain)
+constexpr int kAccStages = 2;                          // TMEM accumulator stages
+constexpr int kImageW = kSlices * kSliceBytesW;        // 96 KiB
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*alignment slack*/ + 512 /*barriers*/;
+constexpr int kFillWarps = 8, kDrainWarps = 4;
+constexpr int kFillThreads = kFillWarps * 32, kDrainThreads = kDrainWarps * 32;
+constexpr int kThreads = kFillThreads + 32 + kDrainThreads;   // 416
+constexpr int kTmemCols = 512;     // W slices: 3 x 64 columns (bf16 pairs); accumulators: columns 256.. : 2 stages x (A0, A1) x 64
+constexpr int kTmemAcc = 256;
+constexpr int kPrefetch = 5;        // tiles of L2 prefetch distance per CTA
 
 // Software bit deposit: tile number -> amplitude base (same role as TileGeo::tile)
 struct Deposit {
@@ -73,22 +79,26 @@ struct Deposit {
 
 struct Params {
   // tile bit t (ascending physical position) -> physical position, and its role: index bit of the
-  // block index j (0..5) or of the rest index n (0..5).  Tile bits 0..2 are physical 0..2 = n0..n2.
+  // block index j (0..5) or of the rest index n (0..5).
   int pos[kTileBits];
   int j_of[kTileBits];   // -1 if the tile bit is a rest bit
   int n_of[kTileBits];   // -1 if the tile bit is a block bit
+  // n0..n2 select the 8 amplitudes of one 16-byte bf16 chunk; the other nine tile bits, ascending, are the item bits
+  // (thread / iteration), so that consecutive threads walk through consecutive memory.  `fast`: n0 is physical
+  // position 0 and n1, n2 are the two HIGHEST rest bits -- an item is four 128-bit accesses, and a warp instruction
+  // covers whole 256-byte runs (positions 1..4 are thread bits).  Otherwise (position 0 belongs to the block) n0..n2 are
+  // the three highest rest bits and an item is eight 64-bit accesses, again contiguous across the warp.
+  int item_tb[9];
+  int elem_off[8];       // amplitude offset of element e of an item (deposit of e into the positions of n0..n2)
+  int fast;
   Deposit tile;          // tile number -> amplitude base over the other n - 12 positions
   uint64_t ntiles;
-  const uint8_t* w_image;  // 96 KiB: the three W slices in their shared-memory byte image (host: make_w_image)
+  const uint32_t* w_image; // 96 KiB: [slice][row mu][64 words], word k2 = (bf16 of column 2 k2) | (bf16 of column 2 k2 + 1) << 16
   int* error_flag;         // set to 1 by a watchdog if a barrier wait times out
+  int products;            // 8: all slice products but p2 * p2;  6: also without p1 * p2, p2 * p1 (2^-24 relative each)
 };
 
 // ------------------------------------------------------------------ byte images (host and device)
-// element (m, k) of a W slice (A operand, K-major SW128, bf16)
-__host__ __device__ __forceinline__ uint32_t w_byte(int m, int k) {
-  const int kb = k >> 6, kk = k & 63;
-  return (uint32_t)(kb * 16384 + (m >> 3) * 1024 + (m & 7) * 128 + ((((kk >> 3) ^ (m & 7)) & 7) << 4) + (kk & 7) * 2);
-}
 // 16-byte chunk holding n = 8 q .. 8 q + 7 of row kappa of an X slice (B operand, MN-major SW128, bf16)
 __host__ __device__ __forceinline__ uint32_t x_chunk_byte(int kappa, int q) {
   return (uint32_t)((kappa >> 3) * 1024 + (kappa & 7) * 128 + (((q ^ (kappa & 7)) & 7) << 4));
@@ -144,6 +154,27 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// A operand from tensor memory (lanes = rows, 32-bit columns = pairs of bf16 along K)
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 registers per thread -> 32 consecutive 32-bit columns of the thread's lane
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -179,20 +210,22 @@ __device__ __forceinline__ uint32_t pack_hi16(float a, float b) {
   return __byte_perm(__float_as_uint(a), __float_as_uint(b), 0x7632);
 }
 
-// per-thread addressing of the 4 items (8 consecutive amplitudes each) a fill / drain thread owns
+// per-thread addressing of the NI items (8 consecutive amplitudes each) a fill / drain thread of a group of
+// NT threads owns: item = it * NT + t, 9 bits <-> the item tile bits (Params::item_tb)
+template <int NI, int NT>
 struct ItemAddr {
-  uint64_t goff[4];   // amplitude offset inside the tile span
-  uint32_t soff[4];   // byte offset of the item's 16-byte chunk in row (c = 0, j) of an X slice
-  __device__ __forceinline__ void init(const Params& p, int t128) {
+  uint64_t goff[NI];   // amplitude offset inside the tile span
+  uint32_t soff[NI];   // byte offset of the item's 16-byte chunk in row (c = 0, j) of an X slice
+  __device__ __forceinline__ void init(const Params& p, int t) {
 #pragma unroll
-    for (int it = 0; it < 4; it++) {
-      const int item = it * 128 + t128;  // 9 bits <-> tile bits 3..11
+    for (int it = 0; it < NI; it++) {
+      const int item = it * NT + t;
       uint64_t g = 0;
       int j = 0, n = 0;
 #pragma unroll
       for (int b = 0; b < 9; b++) {
         if ((item >> b) & 1) {
-          const int tb = b + 3;
+          const int tb = p.item_tb[b];
           g |= 1ull << p.pos[tb];
           if (p.j_of[tb] >= 0) j |= 1 << p.j_of[tb]; else n |= 1 << p.n_of[tb];
         }
@@ -203,81 +236,162 @@ struct ItemAddr {
   }
 };
 
+// the 8 amplitudes of an item: four 128-bit accesses (fast: elements 2h, 2h+1 are adjacent) or eight 64-bit ones
+__device__ __forceinline__ void load_item(const float2* __restrict__ src, const Params& p, float4 (&v)[4]) {
+  if (p.fast) {
+#pragma unroll
+    for (int h = 0; h < 4; h++) v[h] = __ldcs((const float4*)(src + p.elem_off[2 * h]));
+  } else {
+#pragma unroll
+    for (int h = 0; h < 4; h++) {
+      const float2 a = __ldcs(src + p.elem_off[2 * h]), b = __ldcs(src + p.elem_off[2 * h + 1]);
+      v[h] = make_float4(a.x, a.y, b.x, b.y);
+    }
+  }
+}
+__device__ __forceinline__ void prefetch_item(const float2* src, const Params& p) {
+#pragma unroll
+  for (int h = 0; h < 4; h++) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(src + p.elem_off[2 * h]));
+    if (!p.fast) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + p.elem_off[2 * h + 1]));
+  }
+}
+__device__ __forceinline__ void store_item(float2* __restrict__ dst, const Params& p, const float4 (&v)[4]) {
+  if (p.fast) {
+#pragma unroll
+    for (int h = 0; h < 4; h++) __stcs((float4*)(dst + p.elem_off[2 * h]), v[h]);
+  } else {
+#pragma unroll
+    for (int h = 0; h < 4; h++) {
+      __stcs(dst + p.elem_off[2 * h], make_float2(v[h].x, v[h].y));
+      __stcs(dst + p.elem_off[2 * h + 1], make_float2(v[h].z, v[h].w));
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------ the kernel
 // state: 2^n interleaved (re, im) f32 pairs, updated in place: every group of 64 amplitudes over the block
 // qubits is multiplied by W.
+//
+// Warp roles (416 threads, one CTA per SM, persistent over tiles):
+//   warps 0-7   fill  : HBM -> registers (next tile prefetched while this one is sliced) -> tile max -> slices ->
+//                       smem stage (4 stages), arrive `full`
+//   warp  8     MMA   : one lane issues 48 / 64 tcgen05.mma per tile (A = W slices in TMEM, B = X slices in smem),
+//                       tcgen05.commit -> `mma_done`
+//   warps 9-12  drain : tcgen05.ld A0, A1 -> D = A0 + A1 -> smem staging (the stage's own, now dead, X slices) ->
+//                       HBM; arrive `tmem_empty` (2 accumulator stages) and `empty`
 __global__ void __launch_bounds__(kThreads, 1) k_tc_block_fwd(float2* __restrict__ state, const __grid_constant__ Params p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B atoms: 1024-byte aligned
-  uint8_t* sm_w = smem;
-  uint8_t* sm_x = smem + kSmemW;
-  uint64_t* bars = (uint64_t*)(smem + kSmemW + kStages * kStageBytes);
-  uint64_t* full = bars;            // [2] fill -> MMA            (128 arrivals)
-  uint64_t* empty = bars + 2;       // [2] drain -> fill          (128 arrivals)
-  uint64_t* mma_done = bars + 4;    // [2] MMA -> drain           (tcgen05.commit)
-  uint64_t* tmem_empty = bars + 6;  // [2] drain -> MMA           (128 arrivals)
-  uint32_t* tmem_slot = (uint32_t*)(bars + 8);
-  float* sm_max = (float*)(bars + 9);  // [4] warp maxima of the fill group
+  // SWIZZLE_128B atoms: 1024-byte aligned (pointer arithmetic on the array keeps the shared state space: a cast
+  // through uintptr_t made every access a generic LD / ST)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sm_x = smem;
+  uint64_t* bars = (uint64_t*)(smem + kStages * kStageBytes);
+  uint64_t* full = bars;                       // [kStages]    fill -> MMA    (256 arrivals)
+  uint64_t* empty = bars + kStages;            // [kStages]    drain -> fill  (128 arrivals)
+  uint64_t* mma_done = bars + 2 * kStages;     // [kStages]    MMA -> drain   (tcgen05.commit)
+  uint64_t* tmem_empty = bars + 3 * kStages;   // [kAccStages] drain -> MMA   (128 arrivals)
+  uint32_t* tmem_slot = (uint32_t*)(bars + 3 * kStages + kAccStages);
+  float* sm_max = (float*)(tmem_slot + 2);     // [2][8] warp maxima of the fill group (double-buffered by tile parity)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   // ---- one-time setup
-  for (int i = threadIdx.x; i < kSmemW / 16; i += kThreads)
-    ((uint4*)sm_w)[i] = __ldg((const uint4*)p.w_image + i);
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; s++) {
-      mbar_init(&full[s], 128);
-      mbar_init(&empty[s], 128);
+      mbar_init(&full[s], kFillThreads);
+      mbar_init(&empty[s], kDrainThreads);
       mbar_init(&mma_done[s], 1);
-      mbar_init(&tmem_empty[s], 128);
     }
+    for (int s = 0; s < kAccStages; s++) mbar_init(&tmem_empty[s], kDrainThreads);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) {
+  if (warp == kFillWarps) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
-  fence_async_smem();   // the W image was written through the generic proxy, the tensor core reads through the async proxy
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (warp > kFillWarps) {
+    // W slices -> tensor memory: lane = row mu, column = pair of bf16 along K (64 columns per slice)
+    const int q4 = warp & 3, mu = q4 * 32 + lane;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q4 * 32) << 16);
+#pragma unroll 1
+    for (int sl = 0; sl < kSlices; sl++) {
+#pragma unroll
+      for (int half = 0; half < 2; half++) {
+        const uint4* src = (const uint4*)(p.w_image + ((size_t)sl * kDim + mu) * 64 + half * 32);
+        uint32_t r[32];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          const uint4 t = __ldg(src + k);
+          r[4 * k] = t.x; r[4 * k + 1] = t.y; r[4 * k + 2] = t.z; r[4 * k + 3] = t.w;
+        }
+        tmem_st32(lane_addr + sl * 64 + half * 32, r);
+      }
+    }
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
 
-  if (warp < 4) {
+  if (warp < kFillWarps) {
     // =========================================================================== fill
-    const int t128 = threadIdx.x;
-    ItemAddr ia;
-    ia.init(p, t128);
+    const int t = threadIdx.x;
+    ItemAddr<2, kFillThreads> ia;
+    ia.init(p, t);
+    // L2 prefetch of the first tiles of this CTA
+    for (int k = 0; k < kPrefetch; k++) {
+      const uint64_t tl = blockIdx.x + (uint64_t)k * gridDim.x;
+      if (tl < p.ntiles) {
+        const float2* src = state + p.tile(tl);
+#pragma unroll
+        for (int it = 0; it < 2; it++) prefetch_item(src + ia.goff[it], p);
+      }
+    }
     uint32_t it_count = 0;
     for (uint64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, it_count++) {
-      const int s = it_count & 1;
-      const uint32_t use = it_count >> 1;
-      if (use > 0) mbar_wait(&empty[s], (use - 1) & 1, p.error_flag);
-      const float4* src = (const float4*)(state + p.tile(tile));
-      float4 v[4][4];
+      const int s = it_count % kStages;
+      const uint32_t use = it_count / kStages;
+      // This tile comes out of L2: it was prefetched kPrefetch tiles ago.  (No loads may be in flight across the
+      // fence.proxy.async at the end of the iteration -- the fence waits for them: a register prefetch of the next
+      // tile put a full HBM latency into every tile, profiles/r2_tc_fwd_28q_v3_ncu.txt.)
+      float4 v[2][4];
+      {
+        const float2* src = state + p.tile(tile);
 #pragma unroll
-      for (int it = 0; it < 4; it++)
+        for (int it = 0; it < 2; it++) load_item(src + ia.goff[it], p, v[it]);
+      }
+      if (tile + (uint64_t)kPrefetch * gridDim.x < p.ntiles) {
+        const float2* src = state + p.tile(tile + (uint64_t)kPrefetch * gridDim.x);
 #pragma unroll
-        for (int h = 0; h < 4; h++) v[it][h] = __ldcs(src + (ia.goff[it] >> 1) + h);
+        for (int it = 0; it < 2; it++) prefetch_item(src + ia.goff[it], p);
+      }
       float mx = 0.f;
 #pragma unroll
-      for (int it = 0; it < 4; it++)
+      for (int it = 0; it < 2; it++)
 #pragma unroll
         for (int h = 0; h < 4; h++)
           mx = fmaxf(fmaxf(mx, fmaxf(fabsf(v[it][h].x), fabsf(v[it][h].y))), fmaxf(fabsf(v[it][h].z), fabsf(v[it][h].w)));
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-      if (lane == 0) sm_max[warp] = mx;
-      named_bar(1, 128);
-      mx = fmaxf(fmaxf(sm_max[0], sm_max[1]), fmaxf(sm_max[2], sm_max[3]));
-      named_bar(1, 128);   // sm_max may be overwritten by the next tile only after everyone has read it
+      float* mxbuf = sm_max + (it_count & 1) * 8;
+      if (lane == 0) mxbuf[warp] = mx;
+      named_bar(1, kFillThreads);    // (the buffer of the tile before last is free again: one barrier per tile suffices)
+      mx = fmaxf(fmaxf(fmaxf(mxbuf[0], mxbuf[1]), fmaxf(mxbuf[2], mxbuf[3])), fmaxf(fmaxf(mxbuf[4], mxbuf[5]), fmaxf(mxbuf[6], mxbuf[7])));
+      // 9-bit slices: grids 2^(E - 8), 2^(E - 17), 2^(E - 26) with 2^E > max: |k_i| <= 256 is still exact in bf16
+      // (8 significant bits) and the leading products stay exact: 128 * 2^16 = 2^23 < 2^24
       uint32_t bexp = (__float_as_uint(mx) >> 23) & 0xffu;
-      bexp = bexp < 24u ? 24u : (bexp > 230u ? 230u : bexp);
-      const uint32_t m0b = ((bexp + 17u) << 23) | 0x400000u;   // 1.5 * 2^(E + 16), 2^E > max
-      const float m0 = __uint_as_float(m0b), m1 = __uint_as_float(m0b - (8u << 23)), m2 = __uint_as_float(m0b - (16u << 23));
+      bexp = bexp < 32u ? 32u : (bexp > 230u ? 230u : bexp);
+      const uint32_t m0b = ((bexp + 16u) << 23) | 0x400000u;   // 1.5 * 2^(E + 15), 2^E > max
+      const float m0 = __uint_as_float(m0b), m1 = __uint_as_float(m0b - (9u << 23)), m2 = __uint_as_float(m0b - (18u << 23));
+      if (use > 0) mbar_wait(&empty[s], (use - 1) & 1, p.error_flag);
       uint8_t* stage = sm_x + s * kStageBytes;
 #pragma unroll
-      for (int it = 0; it < 4; it++) {
+      for (int it = 0; it < 2; it++) {
         float re[8], im[8];
 #pragma unroll
         for (int h = 0; h < 4; h++) {
@@ -301,34 +415,34 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_block_fwd(float2* __restrict
       fence_async_smem();
       mbar_arrive(&full[s]);
     }
-  } else if (warp == 4) {
+  } else if (warp == kFillWarps) {
     // =========================================================================== MMA issue
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(kDim, kN);
-      const uint32_t w_addr = smem_u32(sm_w), x_addr = smem_u32(sm_x);
+      const uint32_t x_addr = smem_u32(sm_x);
       uint32_t it_count = 0;
       for (uint64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, it_count++) {
-        const int s = it_count & 1;
-        const uint32_t use = it_count >> 1;
+        const int s = it_count % kStages, as = it_count % kAccStages;
+        const uint32_t use = it_count / kStages, ause = it_count / kAccStages;
         mbar_wait(&full[s], use & 1, p.error_flag);
-        if (use > 0) mbar_wait(&tmem_empty[s], (use - 1) & 1, p.error_flag);
+        if (ause > 0) mbar_wait(&tmem_empty[as], (ause - 1) & 1, p.error_flag);
         tc_fence_after();
-        const uint32_t acc0 = tmem_base + (uint32_t)(s * 2 * kN), acc1 = acc0 + kN;
+        const uint32_t acc0 = tmem_base + kTmemAcc + (uint32_t)(as * 2 * kN), acc1 = acc0 + kN;
         const uint32_t xs = x_addr + s * kStageBytes;
-        // (W slice, X slice) products: (0,0) alone into A0 (exact), the seven lower-order ones into A1
+        // (W slice, X slice) products: (0,0) alone into A0 (exact), the lower-order ones into A1
         bool first1 = true;
 #pragma unroll
         for (int pw = 0; pw < 3; pw++) {
 #pragma unroll
           for (int px = 0; px < 3; px++) {
-            if (pw == 2 && px == 2) continue;
+            if (pw + px >= 4) continue;
+            if (pw + px == 3 && p.products < 8) continue;
             const bool lead = (pw == 0 && px == 0);
 #pragma unroll
-            for (int ks = 0; ks < 8; ks++) {   // K = 16 per instruction
-              const uint64_t ad = make_desc(w_addr + pw * kSliceBytesW + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024);
+            for (int ks = 0; ks < 8; ks++) {   // K = 16 per instruction = 8 TMEM columns of A, 16 rows of B
               const uint64_t bd = make_desc(xs + px * kSliceBytesX + ks * 2048, 1024, 1024);
               const uint32_t accumulate = lead ? (ks > 0) : !(first1 && ks == 0);
-              umma_bf16(lead ? acc0 : acc1, ad, bd, idesc, accumulate);
+              umma_bf16_ts(lead ? acc0 : acc1, tmem_base + (uint32_t)(pw * 64 + ks * 8), bd, idesc, accumulate);
             }
             if (!lead) first1 = false;
           }
@@ -338,18 +452,18 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_block_fwd(float2* __restrict
     }
   } else {
     // =========================================================================== drain
-    const int t128 = threadIdx.x - 160;
-    const int q4 = warp & 3;                 // TMEM lane quarter this warp may read
+    const int t128 = threadIdx.x - (kFillThreads + 32);
+    const int q4 = warp & 3;                 // TMEM lane quarter this warp may access
     const int mu = q4 * 32 + lane;           // output row (c', i)
-    ItemAddr ia;
+    ItemAddr<4, kDrainThreads> ia;
     ia.init(p, t128);
     uint32_t it_count = 0;
     for (uint64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, it_count++) {
-      const int s = it_count & 1;
-      const uint32_t use = it_count >> 1;
+      const int s = it_count % kStages, as = it_count % kAccStages;
+      const uint32_t use = it_count / kStages;
       mbar_wait(&mma_done[s], use & 1, p.error_flag);
       tc_fence_after();
-      const uint32_t lane_addr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(s * 2 * kN);
+      const uint32_t lane_addr = tmem_base + ((uint32_t)(q4 * 32) << 16) + kTmemAcc + (uint32_t)(as * 2 * kN);
       uint8_t* stage = sm_x + s * kStageBytes;    // the X slices of this stage are dead: staging for D
 #pragma unroll
       for (int half = 0; half < 2; half++) {      // n = 32 half .. 32 half + 31
@@ -365,39 +479,273 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_block_fwd(float2* __restrict
         }
       }
       tc_fence_before();
-      mbar_arrive(&tmem_empty[s]);                // the accumulators of this stage may be overwritten
-      named_bar(2, 128);
-      float4* dst = (float4*)(state + p.tile(tile));
+      mbar_arrive(&tmem_empty[as]);               // the accumulators of this stage may be overwritten
+      named_bar(2, kDrainThreads);
+      float2* dst = state + p.tile(tile);
 #pragma unroll
       for (int it = 0; it < 4; it++) {
         const float4 r0 = *(const float4*)(stage + ia.soff[it]);
         const float4 r1 = *(const float4*)(stage + kSliceBytesX + ia.soff[it]);
         const float4 i0 = *(const float4*)(stage + ia.soff[it] + 8192u);
         const float4 i1 = *(const float4*)(stage + kSliceBytesX + ia.soff[it] + 8192u);
-        float4* d = dst + (ia.goff[it] >> 1);
-        __stcs(d + 0, make_float4(r0.x, i0.x, r0.y, i0.y));
-        __stcs(d + 1, make_float4(r0.z, i0.z, r0.w, i0.w));
-        __stcs(d + 2, make_float4(r1.x, i1.x, r1.y, i1.y));
-        __stcs(d + 3, make_float4(r1.z, i1.z, r1.w, i1.w));
+        const float4 o[4] = {make_float4(r0.x, i0.x, r0.y, i0.y), make_float4(r0.z, i0.z, r0.w, i0.w),
+                             make_float4(r1.x, i1.x, r1.y, i1.y), make_float4(r1.z, i1.z, r1.w, i1.w)};
+        store_item(dst + ia.goff[it], p, o);
       }
-      named_bar(2, 128);                          // every drain thread has read its staging rows
+      named_bar(2, kDrainThreads);                // every drain thread has read its staging rows
       mbar_arrive(&empty[s]);
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == kFillWarps) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
   }
 }
 
+// ------------------------------------------------------------------------------------ gradient kernel
+// Block gradient of the reverse pass: with a = the state BEFORE the block (already un-computed) and b = the
+// adjoint AFTER the block (not yet pulled back),
+//
+//     P[mu, nu] = sum over every group of 64 amplitudes and every rest index n of  B~[mu, n] * A~[nu, n]
+//
+// (B~, A~ the real-ified 128-row forms), from which G_W[i, j] = sum b[i] a[j] (no conjugation, the convention of
+// src/primitives.cu:323-329) is  Re = P[i, j] - P[64 + i, 64 + j],  Im = P[i, 64 + j] + P[64 + i, j].
+// One tcgen05.mma chain per tile: M = 128 (rows of b), N = 128 (rows of a), K = 64 (n), both operands K-major --
+// the X-slice layout of the forward kernel read along its rows.  9-bit slices as in the forward kernel; the leading
+// product p0(b) * p0(a) accumulates exactly in A0 as long as the grids of consecutive tiles agree (a running maximum
+// of the tile maxima keeps them equal after the first tiles of a CTA) and the sum stays below 2^24 grid units
+// (64 * 2^16 = 2^22 per tile in the worst case; the window is flushed every kFlush = 4 tiles); the five
+// lower-order products go to A1.  A flush adds A0 + A1 into the
+// CTA's private f32 partial in global memory (single writer per element: deterministic); the partials are summed
+// in double by k_tc_grad_reduce.
+constexpr int kGradStageBytes = 2 * kStageBytes;   // b slices, then a slices: 96 KiB
+constexpr int kGradStages = 2;
+constexpr int kGradSmemBytes = kGradStages * kGradStageBytes + 1024 + 512;
+constexpr int kFlush = 4;
+
+struct GradParams {
+  Params geo;          // pos / j_of / n_of / tile / ntiles / error_flag (w_image, products unused)
+  float* partials;     // [gridDim.x][128][128], zero on entry
+};
+
+template <int SEL>   // fill one buffer's slices of a stage from registers
+__device__ __forceinline__ void fill_slices(const float4 (&v)[2][4], const uint32_t (&soff)[2], float m0, float m1, float m2,
+                                            uint8_t* slices) {
+#pragma unroll
+  for (int it = 0; it < 2; it++) {
+    float re[8], im[8];
+#pragma unroll
+    for (int h = 0; h < 4; h++) {
+      re[2 * h] = v[it][h].x; im[2 * h] = v[it][h].y;
+      re[2 * h + 1] = v[it][h].z; im[2 * h + 1] = v[it][h].w;
+    }
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+      float q0[8], q1[8], q2[8];
+#pragma unroll
+      for (int e = 0; e < 8; e++) slice3(c ? im[e] : re[e], m0, m1, m2, q0[e], q1[e], q2[e]);
+      const uint32_t off = soff[it] + (uint32_t)c * 8192u;
+      *(uint4*)(slices + 0 * kSliceBytesX + off) =
+          make_uint4(pack_hi16(q0[0], q0[1]), pack_hi16(q0[2], q0[3]), pack_hi16(q0[4], q0[5]), pack_hi16(q0[6], q0[7]));
+      *(uint4*)(slices + 1 * kSliceBytesX + off) =
+          make_uint4(pack_hi16(q1[0], q1[1]), pack_hi16(q1[2], q1[3]), pack_hi16(q1[4], q1[5]), pack_hi16(q1[6], q1[7]));
+      *(uint4*)(slices + 2 * kSliceBytesX + off) =
+          make_uint4(pack_hi16(q2[0], q2[1]), pack_hi16(q2[2], q2[3]), pack_hi16(q2[4], q2[5]), pack_hi16(q2[6], q2[7]));
+    }
+  }
+}
+
+__device__ __forceinline__ float tile_max8(const float4 (&v)[2][4], float* mxbuf, int warp, int lane, int bar_id) {
+  float mx = 0.f;
+#pragma unroll
+  for (int it = 0; it < 2; it++)
+#pragma unroll
+    for (int h = 0; h < 4; h++)
+      mx = fmaxf(fmaxf(mx, fmaxf(fabsf(v[it][h].x), fabsf(v[it][h].y))), fmaxf(fabsf(v[it][h].z), fabsf(v[it][h].w)));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) mxbuf[warp] = mx;
+  named_bar(bar_id, kFillThreads);
+  return fmaxf(fmaxf(fmaxf(mxbuf[0], mxbuf[1]), fmaxf(mxbuf[2], mxbuf[3])), fmaxf(fmaxf(mxbuf[4], mxbuf[5]), fmaxf(mxbuf[6], mxbuf[7])));
+}
+
+// magic numbers of the 9-bit slicing (grids 2^(E - 8), 2^(E - 17), 2^(E - 26), 2^E > max), see k_tc_block_fwd
+__device__ __forceinline__ void magic_of(uint32_t bexp, float& m0, float& m1, float& m2) {
+  bexp = bexp < 32u ? 32u : (bexp > 230u ? 230u : bexp);
+  const uint32_t m0b = ((bexp + 16u) << 23) | 0x400000u;
+  m0 = __uint_as_float(m0b);
+  m1 = __uint_as_float(m0b - (9u << 23));
+  m2 = __uint_as_float(m0b - (18u << 23));
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+    k_tc_block_grad(const float2* __restrict__ a_state, const float2* __restrict__ b_state, const __grid_constant__ GradParams gp) {
+  const Params& p = gp.geo;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = (uint64_t*)(smem + kGradStages * kGradStageBytes);
+  uint64_t* full = bars;            // [2] fill -> MMA  (256 arrivals)
+  uint64_t* empty = bars + 2;       // [2] MMA -> fill  (tcgen05.commit: the MMAs reading the stage are done)
+  uint64_t* acc_done = bars + 4;    // [2] MMA -> drain (tcgen05.commit at the end of a flush window)
+  uint64_t* acc_empty = bars + 6;   // [2] drain -> MMA (128 arrivals)
+  uint32_t* tmem_slot = (uint32_t*)(bars + 8);
+  float* sm_max = (float*)(tmem_slot + 2);   // [4][8]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 2; s++) {
+      mbar_init(&full[s], kFillThreads);
+      mbar_init(&empty[s], 1);
+      mbar_init(&acc_done[s], 1);
+      mbar_init(&acc_empty[s], kDrainThreads);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kFillWarps) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  // tiles of this CTA and flush windows
+  const uint64_t my_tiles = p.ntiles > (uint64_t)blockIdx.x ? (p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  if (warp < kFillWarps) {
+    // =========================================================================== fill (b slices, then a slices)
+    const int t = threadIdx.x;
+    ItemAddr<2, kFillThreads> ia;
+    ia.init(p, t);
+    auto load = [&](const float2* base, uint64_t tile, float4 (&v)[2][4]) {
+      const float2* src = base + p.tile(tile);
+#pragma unroll
+      for (int it = 0; it < 2; it++) load_item(src + ia.goff[it], p, v[it]);
+    };
+    auto prefetch = [&](uint64_t tile) {
+      const uint64_t base = p.tile(tile);
+#pragma unroll
+      for (int it = 0; it < 2; it++) {
+        prefetch_item(a_state + base + ia.goff[it], p);
+        prefetch_item(b_state + base + ia.goff[it], p);
+      }
+    };
+    for (int k = 0; k < kPrefetch; k++)
+      if (blockIdx.x + (uint64_t)k * gridDim.x < p.ntiles) prefetch(blockIdx.x + (uint64_t)k * gridDim.x);
+    uint32_t e_run_a = 0, e_run_b = 0;
+    uint32_t it_count = 0;
+    for (uint64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, it_count++) {
+      const int s = it_count & 1;
+      const uint32_t use = it_count >> 1;
+      uint8_t* stage = smem + s * kGradStageBytes;
+      float4 vb[2][4], va[2][4];
+      load(b_state, tile, vb);      // out of L2 (prefetched kPrefetch tiles ago); nothing in flight across the fence below
+      load(a_state, tile, va);
+      if (tile + (uint64_t)kPrefetch * gridDim.x < p.ntiles) prefetch(tile + (uint64_t)kPrefetch * gridDim.x);
+      float mx = tile_max8(vb, sm_max + ((it_count & 1) * 2 + 0) * 8, warp, lane, 1);
+      e_run_b = max(e_run_b, (__float_as_uint(mx) >> 23) & 0xffu);
+      float m0, m1, m2;
+      magic_of(e_run_b, m0, m1, m2);
+      if (use > 0) mbar_wait(&empty[s], (use - 1) & 1, p.error_flag);
+      fill_slices<0>(vb, ia.soff, m0, m1, m2, stage);
+      mx = tile_max8(va, sm_max + ((it_count & 1) * 2 + 1) * 8, warp, lane, 1);
+      e_run_a = max(e_run_a, (__float_as_uint(mx) >> 23) & 0xffu);
+      magic_of(e_run_a, m0, m1, m2);
+      fill_slices<1>(va, ia.soff, m0, m1, m2, stage + kStageBytes);
+      fence_async_smem();
+      mbar_arrive(&full[s]);
+    }
+  } else if (warp == kFillWarps) {
+    // =========================================================================== MMA issue
+    if (lane == 0) {
+      // D f32, A / B bf16, both K-major, M = N = 128
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint32_t base = smem_u32(smem);
+      for (uint32_t it = 0; it < (uint32_t)my_tiles; it++) {
+        const int s = it & 1;
+        const uint32_t use = it >> 1, win = it / kFlush, as = win & 1;
+        const bool first = (it % kFlush) == 0, last = (it % kFlush) == kFlush - 1 || it + 1 == (uint32_t)my_tiles;
+        mbar_wait(&full[s], use & 1, p.error_flag);
+        if (first && win >= 2) mbar_wait(&acc_empty[as], ((win >> 1) - 1) & 1, p.error_flag);
+        tc_fence_after();
+        const uint32_t acc0 = tmem_base + as * 256u, acc1 = acc0 + 128u;
+        const uint32_t bs = base + s * kGradStageBytes, as_ = bs + kStageBytes;
+        bool first1 = true;
+#pragma unroll
+        for (int pb = 0; pb < 3; pb++) {
+#pragma unroll
+          for (int pa = 0; pa < 3; pa++) {
+            if (pb + pa >= 3) continue;      // orders 0, 1, 2: (0,0) | (0,1) (1,0) | (0,2) (1,1) (2,0)
+            const bool lead = (pb == 0 && pa == 0);
+#pragma unroll
+            for (int ks = 0; ks < 4; ks++) {   // K = 16 columns n per instruction: 32 bytes along the 128-byte rows
+              const uint64_t ad = make_desc(bs + pb * kSliceBytesX + ks * 32, 16, 1024);
+              const uint64_t bd = make_desc(as_ + pa * kSliceBytesX + ks * 32, 16, 1024);
+              const uint32_t accumulate = lead ? !(first && ks == 0) : !(first && first1 && ks == 0);
+              umma_bf16(lead ? acc0 : acc1, ad, bd, idesc, accumulate);
+            }
+            if (!lead) first1 = false;
+          }
+        }
+        umma_commit(&empty[s]);
+        if (last) umma_commit(&acc_done[as]);
+      }
+    }
+  } else {
+    // =========================================================================== drain: flush windows
+    const int q4 = warp & 3, mu = q4 * 32 + lane;
+    float* mine = gp.partials + ((size_t)blockIdx.x * kDim + mu) * kDim;
+    const uint32_t nwin = (uint32_t)((my_tiles + kFlush - 1) / kFlush);
+    for (uint32_t win = 0; win < nwin; win++) {
+      const uint32_t as = win & 1;
+      mbar_wait(&acc_done[as], (win >> 1) & 1, p.error_flag);
+      tc_fence_after();
+      const uint32_t lane_addr = tmem_base + ((uint32_t)(q4 * 32) << 16) + as * 256u;
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ch++) {
+        float a0[32], a1[32];
+        tmem_ld32(lane_addr + ch * 32, a0);
+        tmem_ld32(lane_addr + 128 + ch * 32, a1);
+        tmem_ld_wait();
+        float4* dst = (float4*)(mine + ch * 32);
+#pragma unroll
+        for (int g = 0; g < 8; g++) {
+          float4 o = dst[g];
+          o.x += a0[4 * g] + a1[4 * g];
+          o.y += a0[4 * g + 1] + a1[4 * g + 1];
+          o.z += a0[4 * g + 2] + a1[4 * g + 2];
+          o.w += a0[4 * g + 3] + a1[4 * g + 3];
+          dst[g] = o;
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&acc_empty[as]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kFillWarps) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+  }
+}
+
+// out[k] (+)= sum over CTAs of partials[cta][k], k < 128 * 128, in double
+__global__ void k_tc_grad_reduce(const float* __restrict__ partials, int ncta, double* __restrict__ out, int accumulate) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= kDim * kDim) return;
+  double s = 0;
+  for (int c = 0; c < ncta; c++) s += (double)partials[(size_t)c * kDim * kDim + k];
+  out[k] = accumulate ? out[k] + s : s;
+}
+
 // ------------------------------------------------------------------------------------ host side
-// bf16 slices of v on the grid 2^(E - 7 - 8 i): returns the three slice values (exactly representable in bf16)
+// bf16 slices of v on the grids 2^(E - 8 - 9 i): returns the three slice values (exactly representable in bf16)
 inline void host_slice3(double v, int E, float out[3]) {
   double r = v;
   for (int i = 0; i < 3; i++) {
-    const double g = std::ldexp(1.0, E - 7 - 8 * i);
+    const double g = std::ldexp(1.0, E - 8 - 9 * i);   // 9-bit slices, |k| <= 256 (see k_tc_block_fwd)
     const double pi = std::nearbyint(r / g) * g;
     out[i] = (float)pi;
     r -= pi;
@@ -409,15 +757,16 @@ inline uint16_t host_bf16_bits(float f) {
   return (uint16_t)(u >> 16);   // exact: the slices have at most 8 significant bits
 }
 
-// W: 64 x 64 complex (row-major, double re / im pairs), index bit b of the block index = block qubit j_b.
-// Real-ified R[(c', i), (c, j)]: [[Wr, -Wi], [Wi, Wr]].  Returns the 96 KiB shared-memory image; E_w is chosen so
-// that 2^E_w >= max |entry| (0 for unitaries).
-inline std::vector<uint8_t> make_w_image(const double* w_re_im) {
+// W: 64 x 64 complex (row-major, double re / im pairs), index bit b of the block index = kernel index bit j_b.
+// Real-ified R[(c', i), (c, j)]: [[Wr, -Wi], [Wi, Wr]].  Returns the 96 KiB image [slice][row][64 words] the kernel
+// copies into tensor memory; the slicing grid 2^(E_w - 7) has 2^E_w >= max |entry| (E_w = 0 for unitaries).
+// `odd_low`: development switch for the order of the two bf16 of a 32-bit TMEM column (default: even K index low).
+inline std::vector<uint32_t> make_w_image(const double* w_re_im, bool odd_low = false) {
   double mx = 0;
   for (int i = 0; i < 64 * 64 * 2; i++) mx = std::max(mx, std::fabs(w_re_im[i]));
   int E = 0;
   while (std::ldexp(1.0, E) < mx) E++;
-  std::vector<uint8_t> img(kSmemW, 0);
+  std::vector<uint32_t> img(kImageW / 4, 0u);
   for (int m = 0; m < kDim; m++) {
     for (int k = 0; k < kDim; k++) {
       const int cp = m >> 6, i = m & 63, c = k >> 6, j = k & 63;
@@ -426,20 +775,24 @@ inline std::vector<uint8_t> make_w_image(const double* w_re_im) {
       float sl[3];
       host_slice3(r, E, sl);
       for (int s = 0; s < 3; s++) {
-        const uint16_t b = host_bf16_bits(sl[s]);
-        memcpy(&img[(size_t)s * kSliceBytesW + w_byte(m, k)], &b, 2);
+        const uint32_t b = host_bf16_bits(sl[s]);
+        const bool high = ((k & 1) != 0) != odd_low;
+        img[((size_t)s * kDim + m) * 64 + (k >> 1)] |= high ? (b << 16) : b;
       }
     }
   }
   return img;
 }
 
-// Geometry of a pass: `block` = the 6 physical positions of the block qubits in the order of W's index bits
-// (index bit b <-> block[b]); every position must be >= 3.  Fills pos / j_of / n_of / tile.
+// Geometry of a pass: `block` = the 6 physical positions of the block qubits in the order of the caller's index
+// bits (index bit b <-> block[b]).  Fills pos / j_of / n_of / item_tb / elem_off / tile; w_bit_of_jbit[k] = the
+// caller's index bit that the kernel's block-index bit k stands for.
 inline const char* make_params(const int* block, int n_qubits, Params* p, int* w_bit_of_jbit /* [6] */) {
-  std::vector<int> bits = {0, 1, 2, 3, 4};
+  std::vector<int> bits = {0, 1, 2, 3, 4};   // every tile holds the 5 lowest positions: 256-byte runs in HBM
   for (int b = 0; b < 6; b++) {
-    if (block[b] < 3 || block[b] >= n_qubits) return "block qubits must lie in [3, n).";
+    if (block[b] < 0 || block[b] >= n_qubits) return "block qubit out of range.";
+    for (int c = 0; c < b; c++)
+      if (block[c] == block[b]) return "block qubits must be distinct.";
     if (std::find(bits.begin(), bits.end(), block[b]) == bits.end()) bits.push_back(block[b]);
   }
   for (int q = 5; (int)bits.size() < kTileBits && q < n_qubits; q++)
@@ -447,34 +800,48 @@ inline const char* make_params(const int* block, int n_qubits, Params* p, int* w
   if ((int)bits.size() != kTileBits) return "register too small for a tensor-core pass.";
   std::sort(bits.begin(), bits.end());
   auto is_block = [&](int pos) { return std::find(block, block + 6, pos) != block + 6; };
-  // index bits: tile bits 0..2 are n0..n2; tile bit 3 + i takes n_{3+i} (rest) or j_i (block), so that the three
-  // lowest thread bits always move the swizzled 16-byte slot (bank-conflict-free STS.128 / LDS.128)
-  std::vector<int> rest_pool, block_pool;
-  for (int t = 6; t < kTileBits; t++) (is_block(bits[t]) ? block_pool : rest_pool).push_back(t);
   for (int t = 0; t < kTileBits; t++) {
     p->pos[t] = bits[t];
     p->j_of[t] = p->n_of[t] = -1;
   }
+  // n0..n2: position 0 when it is a rest bit, then the highest rest tile bits (see Params)
+  int nlow[3], nl = 0;
+  if (!is_block(0)) nlow[nl++] = 0;
+  {
+    std::vector<int> high;
+    for (int t = kTileBits - 1; t >= 1 && (int)high.size() < 3 - nl; t--)
+      if (!is_block(bits[t])) high.push_back(t);
+    if ((int)high.size() < 3 - nl) return "internal: fewer than three rest bits.";
+    for (int k = (int)high.size() - 1; k >= 0; k--) nlow[nl++] = high[k];   // ascending
+  }
+  for (int k = 0; k < 3; k++) p->n_of[nlow[k]] = k;
+  p->fast = !is_block(0) ? 1 : 0;
+  for (int e = 0; e < 8; e++) {
+    long off = 0;
+    for (int k = 0; k < 3; k++)
+      if ((e >> k) & 1) off |= 1l << bits[nlow[k]];
+    if (off > 0x7fffffffl) return "tile bit set too spread out.";
+    p->elem_off[e] = (int)off;
+  }
+  // item bits: the other nine tile bits, ascending.  Item bit i < 3 takes n_{3+i} (rest) or j_i (block), so that the
+  // three lowest thread bits always move the swizzled 16-byte slot (bank-conflict-free STS.128 / LDS.128)
+  int ni = 0;
+  for (int t = 0; t < kTileBits; t++)
+    if (t != nlow[0] && t != nlow[1] && t != nlow[2]) p->item_tb[ni++] = t;
   bool n_used[6] = {true, true, true, false, false, false}, j_used[6] = {false, false, false, false, false, false};
-  for (int t = 0; t < 3; t++) p->n_of[t] = t;
   for (int i = 0; i < 3; i++) {
-    const int t = 3 + i;
+    const int t = p->item_tb[i];
     if (is_block(bits[t])) { p->j_of[t] = i; j_used[i] = true; }
     else { p->n_of[t] = 3 + i; n_used[3 + i] = true; }
   }
-  for (int t : rest_pool) {
+  for (int i = 3; i < 9; i++) {
+    const int t = p->item_tb[i];
+    bool* used = is_block(bits[t]) ? j_used : n_used;
     int k = 0;
-    while (k < 6 && n_used[k]) k++;
-    if (k == 6) return "internal: too many rest bits.";
-    p->n_of[t] = k;
-    n_used[k] = true;
-  }
-  for (int t : block_pool) {
-    int k = 0;
-    while (k < 6 && j_used[k]) k++;
-    if (k == 6) return "internal: too many block bits.";
-    p->j_of[t] = k;
-    j_used[k] = true;
+    while (k < 6 && used[k]) k++;
+    if (k == 6) return "internal: index bits exhausted.";
+    (is_block(bits[t]) ? p->j_of[t] : p->n_of[t]) = k;
+    used[k] = true;
   }
   // kernel index bit j_k <-> which index bit of the caller's W
   for (int t = 0; t < kTileBits; t++)
@@ -501,4 +868,5 @@ inline const char* make_params(const int* block, int n_qubits, Params* p, int* w
   p->ntiles = 1ull << (n_qubits - kTileBits);
   return nullptr;
 }
+
 }  // namespace tcb

@@ -318,7 +318,7 @@ inline const char* Circuit::run_seed_group(const DensGroup& g, const std::vector
 // The densities plan_.steps[first..last] belong to one program point: group them into tiled sweeps
 // (singletons and the per-instruction executor keep the streaming kernels).
 inline const char* Circuit::run_dens_run(size_t first, size_t last, const std::vector<long>& dslot) {
-  const qdc::SchedOptions so = sched_options();
+  const qdc::SchedOptions so = base_options();
   if (!opt_batch_dens_ || so.tile_bits == 0 || last == first) {
     for (size_t k = first; k <= last; k++) QDC_TRY(dens_single(plan_.steps[k], dslot));
     return nullptr;
@@ -337,7 +337,7 @@ inline const char* Circuit::run_seed_run(size_t first, size_t last, const std::v
   for (size_t k = last + 1; k-- > first;)
     if (kind_is_diff_dens(insts_[plan_.steps[k].inst].kind)) which.push_back((int)k);
   if (which.empty()) return nullptr;
-  const qdc::SchedOptions so = sched_options();
+  const qdc::SchedOptions so = base_options();
   if (!opt_batch_dens_ || so.tile_bits == 0 || which.size() == 1) {
     for (int k : which) {
       QDC_TRY(seed_single(plan_.steps[k], dp, *live));

@@ -10,6 +10,7 @@
 #include <complex>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <random>
 
 #include "../../differentiable-quantum-circuit-cuda_b200/csrc/tc_block.cuh"
@@ -62,7 +63,8 @@ static void apply_gate_to_rows(std::vector<zc>& w, const zc* g, int hi, int lo) 
   w.swap(out);
 }
 
-static std::vector<uint8_t> image_of(const std::vector<zc>& w, const int* w_bit_of_jbit) {
+static bool g_odd_low = false;
+static std::vector<uint32_t> image_of(const std::vector<zc>& w, const int* w_bit_of_jbit) {
   // kernel index bit k <-> caller index bit w_bit_of_jbit[k]
   auto perm = [&](int idx) {
     int o = 0;
@@ -76,7 +78,7 @@ static std::vector<uint8_t> image_of(const std::vector<zc>& w, const int* w_bit_
       flat[2 * (i * 64 + j)] = v.real();
       flat[2 * (i * 64 + j) + 1] = v.imag();
     }
-  return tcb::make_w_image(flat.data());
+  return tcb::make_w_image(flat.data(), g_odd_low);
 }
 
 int main(int argc, char** argv) {
@@ -85,9 +87,11 @@ int main(int argc, char** argv) {
   const int rounds = argc > 3 ? atoi(argv[3]) : 10;
   int block[6];
   for (int b = 0; b < 6; b++) block[b] = q0 + b;
-  if (argc > 4) {  // scattered block, e.g. "3,4,9,10,17,20"
+  if (argc > 4 && strcmp(argv[4], "-") != 0) {  // scattered block, e.g. "3,4,9,10,17,20"
     if (sscanf(argv[4], "%d,%d,%d,%d,%d,%d", block, block + 1, block + 2, block + 3, block + 4, block + 5) != 6) return 1;
   }
+  const int products = argc > 5 ? atoi(argv[5]) : 8;   // 8 or 6 slice products per block
+  g_odd_low = argc > 6 && atoi(argv[6]) != 0;
   // W = brickwork diamond of 9 gates on the 6 block qubits
   std::vector<zc> w(64 * 64, 0.0);
   for (int i = 0; i < 64; i++) w[i * 64 + i] = 1.0;
@@ -104,15 +108,16 @@ int main(int argc, char** argv) {
   int wbit[6];
   const char* err = tcb::make_params(block, n, &p, wbit);
   if (err) { printf("make_params: %s\n", err); return 1; }
-  std::vector<uint8_t> img = image_of(w, wbit), img_dag = image_of(wdag, wbit);
-  uint8_t *d_img, *d_img_dag;
+  std::vector<uint32_t> img = image_of(w, wbit), img_dag = image_of(wdag, wbit);
+  uint32_t *d_img, *d_img_dag;
+  p.products = products;
   int* d_err;
-  CK(cudaMalloc(&d_img, img.size()));
-  CK(cudaMalloc(&d_img_dag, img.size()));
+  CK(cudaMalloc(&d_img, img.size() * 4));
+  CK(cudaMalloc(&d_img_dag, img.size() * 4));
   CK(cudaMalloc(&d_err, sizeof(int)));
   CK(cudaMemset(d_err, 0, sizeof(int)));
-  CK(cudaMemcpy(d_img, img.data(), img.size(), cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(d_img_dag, img_dag.data(), img.size(), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_img, img.data(), img.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_img_dag, img_dag.data(), img.size() * 4, cudaMemcpyHostToDevice));
   p.error_flag = d_err;
 
   const size_t N = (size_t)1 << n;
@@ -132,7 +137,7 @@ int main(int argc, char** argv) {
   CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
   CK(cudaFuncSetAttribute(tcb::k_tc_block_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, tcb::kSmemBytes));
   const int grid = (int)std::min<uint64_t>(p.ntiles, (uint64_t)sms);
-  auto launch = [&](const uint8_t* image) {
+  auto launch = [&](const uint32_t* image) {
     p.w_image = image;
     tcb::k_tc_block_fwd<<<grid, tcb::kThreads, tcb::kSmemBytes>>>(d_state, p);
   };
@@ -164,23 +169,46 @@ int main(int argc, char** argv) {
       max_val = std::max(max_val, std::abs(s));
     }
   }
-  printf("n=%d block=%d,%d,%d,%d,%d,%d  one block vs host double: max |err| / max |value| = %.3e\n", n, block[0], block[1],
-         block[2], block[3], block[4], block[5], max_err / max_val);
+  printf("n=%d block=%d,%d,%d,%d,%d,%d products=%d odd_low=%d  one block vs host double: max |err| / max |value| = %.3e\n", n, block[0], block[1],
+         block[2], block[3], block[4], block[5], products, (int)g_odd_low, max_err / max_val);
 
-  // ---- 2. drift: (W^dagger W)^rounds must be the identity
-  launch(d_img_dag);
-  for (int r = 1; r < rounds; r++) { launch(d_img); launch(d_img_dag); }
-  CK(cudaGetLastError());
-  CK(cudaDeviceSynchronize());
-  CK(cudaMemcpy(out.data(), d_state, N * sizeof(float2), cudaMemcpyDeviceToHost));
-  double dev = 0, mx = 0, n2 = 0;
-  for (size_t i = 0; i < N; i++) {
-    dev = std::max(dev, (double)std::hypot(out[i].x - h[i].x, out[i].y - h[i].y));
-    mx = std::max(mx, (double)std::hypot(h[i].x, h[i].y));
-    n2 += (double)out[i].x * out[i].x + (double)out[i].y * out[i].y;
+  // ---- 2. drift: `rounds` DIFFERENT random blocks, then their inverses in reverse order (a forward sweep followed by
+  //         its un-computation): the state must come back, the deviation is pure arithmetic error of 2 * rounds blocks
+  {
+    CK(cudaMemcpy(d_state, h.data(), N * sizeof(float2), cudaMemcpyHostToDevice));
+    std::vector<uint32_t*> d_fw(rounds), d_bw(rounds);
+    for (int r = 0; r < rounds; r++) {
+      std::vector<zc> wr(64 * 64, 0.0), wrd(64 * 64);
+      for (int i = 0; i < 64; i++) wr[i * 64 + i] = 1.0;
+      for (auto& pr : pairs) {
+        zc g[16];
+        haar4(g);
+        apply_gate_to_rows(wr, g, pr[0], pr[1]);
+      }
+      for (int i = 0; i < 64; i++) for (int j = 0; j < 64; j++) wrd[i * 64 + j] = std::conj(wr[j * 64 + i]);
+      std::vector<uint32_t> a = image_of(wr, wbit), bimg = image_of(wrd, wbit);
+      CK(cudaMalloc(&d_fw[r], a.size() * 4));
+      CK(cudaMalloc(&d_bw[r], a.size() * 4));
+      CK(cudaMemcpy(d_fw[r], a.data(), a.size() * 4, cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(d_bw[r], bimg.data(), a.size() * 4, cudaMemcpyHostToDevice));
+    }
+    for (int r = 0; r < rounds; r++) launch(d_fw[r]);
+    for (int r = rounds - 1; r >= 0; r--) launch(d_bw[r]);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(out.data(), d_state, N * sizeof(float2), cudaMemcpyDeviceToHost));
+    double dev = 0, mx = 0, n2 = 0, d2 = 0;
+    for (size_t i = 0; i < N; i++) {
+      const double d = std::hypot(out[i].x - h[i].x, out[i].y - h[i].y);
+      dev = std::max(dev, d);
+      d2 += d * d;
+      mx = std::max(mx, (double)std::hypot(h[i].x, h[i].y));
+      n2 += (double)out[i].x * out[i].x + (double)out[i].y * out[i].y;
+    }
+    printf("after %d distinct blocks and their inverses (%d block applications): max |deviation| / max |amplitude| = %.3e, "
+           "||deviation||_2 / ||state||_2 = %.3e, norm^2 - 1 = %.3e\n", rounds, 2 * rounds, dev / mx, std::sqrt(d2), n2 - 1.0);
+    for (int r = 0; r < rounds; r++) { cudaFree(d_fw[r]); cudaFree(d_bw[r]); }
   }
-  printf("after %d blocks (W, W^dagger alternating): max |deviation| / max |amplitude| = %.3e, norm^2 - 1 = %.3e\n",
-         2 * rounds, dev / mx, n2 - 1.0);
 
   // ---- 3. throughput
   cudaEvent_t e0, e1;
@@ -197,8 +225,8 @@ int main(int argc, char** argv) {
   ms /= 2 * reps;
   const double bytes = 2.0 * N * sizeof(float2);
   printf("one block pass: %.3f ms = %.1f GB/s of HBM traffic (read + write); 9 gates per block -> %.2f us per gate, "
-         "%.1f TFLOP/s bf16 tensor (64 MMAs of 128x64x16 per tile)\n",
-         ms, bytes / ms * 1e-6, ms * 1e3 / 9, 64.0 * 2 * 128 * 64 * 16 * (double)p.ntiles / ms * 1e-9);
+         "%.1f TFLOP/s bf16 tensor (%d MMAs of 128x64x16 per tile)\n",
+         ms, bytes / ms * 1e-6, ms * 1e3 / 9, 8.0 * products * 2 * 128 * 64 * 16 * (double)p.ntiles / ms * 1e-9, 8 * products);
   int herr = 0;
   CK(cudaMemcpy(&herr, d_err, sizeof(int), cudaMemcpyDeviceToHost));
   printf("watchdog flag: %d\n", herr);
