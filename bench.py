@@ -297,6 +297,10 @@ def make_circuit(args, world, n_total, precision, workload, depth, opts=None):
         o["soa"] = args.soa
     if precision == "f32" and args.tc >= 0:
         o["tc"] = args.tc
+    if precision == "f32" and args.tc_rev >= 0:
+        o["tc_rev"] = args.tc_rev
+    if precision == "f32" and args.tc_products > 0:
+        o["tc_products"] = args.tc_products
     for key, val in (("rb_policy", args.rb_policy), ("batch_dens", args.batch_dens),
                      ("tile_strategy", args.tile_strategy)):
         if val >= 0:
@@ -381,7 +385,7 @@ def load_peaks():
     return peak, src, float(peaks.get("sm_max_mhz", 1965.0))
 
 
-def roofline_block(prof, dev_ms, steps, precision, local_qubits, kinds, clocks):
+def roofline_block(prof, dev_ms, steps, precision, local_qubits, kinds, clocks, tc_rev=True):
     """Dominant kernel = the category with the most device time.  `achieved` / `frac` follow SURVEY 8(d):
     algorithmic bytes (2*S forward, 4*S reverse PER GATE) over the launch time against the measured HBM copy
     peak -- above 1 when a launch applies several gates.  The binding resource of the tiled passes is the
@@ -421,9 +425,10 @@ def roofline_block(prof, dev_ms, steps, precision, local_qubits, kinds, clocks):
         r["dram_frac"] = round(r["dram_gbs"] / peak, 4)
         r["gates_per_launch"] = round(r["algorithmic_bytes_per_launch"] / float(passes * S), 2)
     if name in ("tc_bwd", "tc_fwd"):
-        # tensor-core fused blocks (csrc/tc_block.cuh): one 64 x 64 block per HBM sweep.  Reverse step of a block =
-        # un-compute (2*S) + block gradient (2*S read) + adjoint pull-back (2*S) = 6*S of real traffic.
-        passes = 6 if name == "tc_bwd" else 2
+        # tensor-core fused blocks (csrc/tc_block.cuh, tc_rev.cuh): one 64 x 64 block per HBM sweep.  Reverse step of a
+        # block = ONE fused sweep over state and adjoint (4*S of real traffic); with option tc_rev = 0 un-compute (2*S) +
+        # block gradient (2*S read) + adjoint pull-back (2*S) = 6*S.
+        passes = (4 if tc_rev else 6) if name == "tc_bwd" else 2
         alg = 4 if name == "tc_bwd" else 2
         tiles = float(1 << (local_qubits - 12))
         mma_flop = 2.0 * 128 * 64 * 16                     # one tcgen05.mma of the block kernel (M 128, N 64, K 16)
@@ -436,7 +441,8 @@ def roofline_block(prof, dev_ms, steps, precision, local_qubits, kinds, clocks):
         tpeak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0)))
         r["bound"] = "hbm"
         r["traffic"] = passes * S
-        r["traffic_source"] = "= %d*S per block (state and adjoint read + written once per kernel of the block)" % passes
+        r["traffic_source"] = ("= %d*S per block (state%s read + written once per kernel of the block)"
+                               % (passes, " and adjoint" if name == "tc_bwd" else ""))
         r["dram_gbs"] = round(passes * S * e["launches"] / sec / 1e9, 1)
         r["dram_frac"] = round(r["dram_gbs"] / peak, 4)
         r["tensor_tflops"] = round(per_tile * tiles * e["launches"] / sec / 1e12, 1)
@@ -506,7 +512,7 @@ def run_workload(args, world, rank, local, precision, workload, local_qubits, de
                                   if "tc_fwd" in prof or "tc_bwd" in prof else "")},
         "effective_hbm_gbs": round(total_alg * world / (dev_ms * 1e-3) / 1e9, 1),
         "effective_hbm_frac": round(total_alg / (dev_ms * 1e-3) / 1e9 / peak, 4),
-        "roofline": roofline_block(prof, dev_ms, steps, precision, local_qubits, kinds, clocks),
+        "roofline": roofline_block(prof, dev_ms, steps, precision, local_qubits, kinds, clocks, tc_rev=args.tc_rev != 0),
         "profile_ms": {k: round(v["ms"], 2) for k, v in sorted(prof.items())},
         "e2e": {"value": round(world * n_gates * steps / wall, 3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h)},
@@ -655,6 +661,8 @@ def main():
     ap.add_argument("--rb-policy", type=int, default=-1, help="fuse=2 forward: 0 never register-block, 1 always, 2 by gate mix (default)")
     ap.add_argument("--batch-dens", type=int, default=-1, help="0: one sweep per density / seed")
     ap.add_argument("--tile-strategy", type=int, default=-1, help="scheduler tiling: 2 window growth with look-ahead (default), 1 window growth, 0 first-fit")
+    ap.add_argument("--tc-rev", type=int, default=-1, help="f32 + tc: 1 fused one-sweep reverse step of a block (4*S), 0 three sweeps (6*S)")
+    ap.add_argument("--tc-products", type=int, default=0, help="f32 + tc: 8 or 6 bf16 slice products per block (0: library default)")
     ap.add_argument("--tc", type=int, default=-1, help="f32: 1 tensor-core fused 6-qubit blocks, 0 FP32-pipe tile kernels only (-1: library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-check", action="store_true", help="skip the parity check that precedes the timed steps")

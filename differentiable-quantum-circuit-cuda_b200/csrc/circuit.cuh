@@ -224,6 +224,7 @@ class Circuit {
   // (tc_exec.cuh / tc_block.cuh); the scheduler then grows 6-position windows
   int opt_tc_ = 0;
   int opt_tc_products_ = 8;   // bf16 slice products per block (tc_block.cuh)
+  int opt_tc_rev_ = 1;        // reverse step of a block: 1 one fused sweep (tc_rev.cuh, 4*S), 0 three sweeps (6*S)
   TcState* tc_ = nullptr;
   int opt_tile_bits_ = 0;  // 0: default for the precision
   int opt_low_bits_ = 0;
@@ -1175,7 +1176,8 @@ class Circuit {
   const char* tc_ensure(size_t image_slots, size_t grad_slots);
   const char* tc_begin(bool backward);
   const char* tc_prepare(const qdc::Step& t, const std::vector<const cplx_t*>& gp, tcb::Params* geo, TcPass* pass);
-  const char* tc_launch_block(cplx_t* buf, const tcb::Params& geo, const std::vector<zc>& w, int form);
+  const char* tc_launch_block(cplx_t* buf, const tcb::Params& geo, const std::vector<zc>& w, int form, bool launch,
+                              tcb::Params* geo_out = nullptr);
   const char* run_tc_forward(const qdc::Step& t, const std::vector<const cplx_t*>& gp, bool uncompute);
   const char* run_tc_backward(const qdc::Step& t, const std::vector<const cplx_t*>& gp);
   const char* tc_finish_backward();

@@ -146,6 +146,8 @@ QDC_EXPORT const char* qdc_circuit_set_option(qdc_circuit* c, const char* key, l
   } else if (strcmp(key, "tc_products") == 0) {
     if (value != 6 && value != 8) return qdc_errf("tc_products must be 6 or 8.");
     c->impl.opt_tc_products_ = (int)value;
+  } else if (strcmp(key, "tc_rev") == 0) {
+    c->impl.opt_tc_rev_ = value != 0;
   } else if (strcmp(key, "max_tile_gates") == 0) {
     if (value < 1 || value > QDC_TILE_MAXG_B) return qdc_errf("max_tile_gates must be in 1..%d.", QDC_TILE_MAXG_B);
     c->impl.opt_max_tile_gates_ = (int)value;

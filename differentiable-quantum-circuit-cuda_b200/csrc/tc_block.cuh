@@ -143,6 +143,25 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_b
   return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
          (1ull << 46) | (2ull << 61);
 }
+// one lane of a converged warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred)
+      :
+      : "memory");
+  return pred != 0;
+}
+// shared-memory matrix descriptors (see make_desc) as a base word plus byte offsets: SBO = 1024 everywhere
+constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return ((smem_addr & 0x3FFFFu) >> 4) | ((lbo_bytes >> 4) << 16);
+}
+__device__ __forceinline__ uint64_t desc_at(uint32_t lo, uint32_t hi, uint32_t byte_off) {
+  return ((uint64_t)hi << 32) | (uint64_t)(lo + (byte_off >> 4));
+}
+
 // instruction descriptor (cute::UMMA::InstrDescriptor), kind::f16: D f32, A / B bf16, A K-major, B MN-major
 __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (0u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
@@ -353,18 +372,18 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_block_fwd(float2* __restrict
       }
     }
     uint32_t it_count = 0;
+    // Software pipeline over registers: the loads of the NEXT tile are issued as soon as this tile's slices have been
+    // taken, so that a whole tile (32 KiB, ~1500 cycles at this SM's share of the HBM bandwidth) is in flight while
+    // the fill fences, waits for its stage and reduces the next maximum.  The L2 prefetch runs kPrefetch tiles ahead.
+    float4 v[2][4];
+    if ((uint64_t)blockIdx.x < p.ntiles) {
+      const float2* src = state + p.tile(blockIdx.x);
+#pragma unroll
+      for (int it = 0; it < 2; it++) load_item(src + ia.goff[it], p, v[it]);
+    }
     for (uint64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, it_count++) {
       const int s = it_count % kStages;
       const uint32_t use = it_count / kStages;
-      // This tile comes out of L2: it was prefetched kPrefetch tiles ago.  (No loads may be in flight across the
-      // fence.proxy.async at the end of the iteration -- the fence waits for them: a register prefetch of the next
-      // tile put a full HBM latency into every tile, profiles/r2_tc_fwd_28q_v3_ncu.txt.)
-      float4 v[2][4];
-      {
-        const float2* src = state + p.tile(tile);
-#pragma unroll
-        for (int it = 0; it < 2; it++) load_item(src + ia.goff[it], p, v[it]);
-      }
       if (tile + (uint64_t)kPrefetch * gridDim.x < p.ntiles) {
         const float2* src = state + p.tile(tile + (uint64_t)kPrefetch * gridDim.x);
 #pragma unroll
@@ -412,23 +431,31 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_block_fwd(float2* __restrict
               make_uint4(pack_hi16(q2[0], q2[1]), pack_hi16(q2[2], q2[3]), pack_hi16(q2[4], q2[5]), pack_hi16(q2[6], q2[7]));
         }
       }
+      if (tile + gridDim.x < p.ntiles) {
+        const float2* src = state + p.tile(tile + gridDim.x);
+#pragma unroll
+        for (int it = 0; it < 2; it++) load_item(src + ia.goff[it], p, v[it]);
+      }
       fence_async_smem();
       mbar_arrive(&full[s]);
     }
   } else if (warp == kFillWarps) {
     // =========================================================================== MMA issue
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(kDim, kN);
-      const uint32_t x_addr = smem_u32(sm_x);
-      uint32_t it_count = 0;
-      for (uint64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, it_count++) {
-        const int s = it_count % kStages, as = it_count % kAccStages;
-        const uint32_t use = it_count / kStages, ause = it_count / kAccStages;
-        mbar_wait(&full[s], use & 1, p.error_flag);
-        if (ause > 0) mbar_wait(&tmem_empty[as], (ause - 1) & 1, p.error_flag);
-        tc_fence_after();
+    // The whole warp runs the loop converged and one ELECTED lane issues: from `if (lane == 0)` ptxas wrapped every
+    // UTCHMMA in a leader-election loop (50-80 cycles per instruction, more than the 32 the tensor pipe needs).
+    constexpr uint32_t idesc = make_idesc(kDim, kN);
+    const uint32_t x_addr = smem_u32(sm_x);
+    const bool all8 = p.products >= 8;
+    uint32_t it_count = 0;
+    for (uint64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, it_count++) {
+      const int s = it_count % kStages, as = it_count % kAccStages;
+      const uint32_t use = it_count / kStages, ause = it_count / kAccStages;
+      mbar_wait(&full[s], use & 1, p.error_flag);
+      if (ause > 0) mbar_wait(&tmem_empty[as], (ause - 1) & 1, p.error_flag);
+      tc_fence_after();
+      if (elect_one()) {
         const uint32_t acc0 = tmem_base + kTmemAcc + (uint32_t)(as * 2 * kN), acc1 = acc0 + kN;
-        const uint32_t xs = x_addr + s * kStageBytes;
+        const uint32_t x_lo = desc_lo(x_addr + s * kStageBytes, 1024);
         // (W slice, X slice) products: (0,0) alone into A0 (exact), the lower-order ones into A1
         bool first1 = true;
 #pragma unroll
@@ -436,11 +463,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_block_fwd(float2* __restrict
 #pragma unroll
           for (int px = 0; px < 3; px++) {
             if (pw + px >= 4) continue;
-            if (pw + px == 3 && p.products < 8) continue;
+            if (pw + px == 3 && !all8) continue;
             const bool lead = (pw == 0 && px == 0);
 #pragma unroll
             for (int ks = 0; ks < 8; ks++) {   // K = 16 per instruction = 8 TMEM columns of A, 16 rows of B
-              const uint64_t bd = make_desc(xs + px * kSliceBytesX + ks * 2048, 1024, 1024);
+              const uint64_t bd = desc_at(x_lo, kDescHi, px * kSliceBytesX + ks * 2048);
               const uint32_t accumulate = lead ? (ks > 0) : !(first1 && ks == 0);
               umma_bf16_ts(lead ? acc0 : acc1, tmem_base + (uint32_t)(pw * 64 + ks * 8), bd, idesc, accumulate);
             }
@@ -449,6 +476,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_block_fwd(float2* __restrict
         }
         umma_commit(&mma_done[s]);
       }
+      __syncwarp();
     }
   } else {
     // =========================================================================== drain
@@ -658,20 +686,20 @@ __global__ void __launch_bounds__(kThreads, 1)
       mbar_arrive(&full[s]);
     }
   } else if (warp == kFillWarps) {
-    // =========================================================================== MMA issue
-    if (lane == 0) {
-      // D f32, A / B bf16, both K-major, M = N = 128
-      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      const uint32_t base = smem_u32(smem);
-      for (uint32_t it = 0; it < (uint32_t)my_tiles; it++) {
-        const int s = it & 1;
-        const uint32_t use = it >> 1, win = it / kFlush, as = win & 1;
-        const bool first = (it % kFlush) == 0, last = (it % kFlush) == kFlush - 1 || it + 1 == (uint32_t)my_tiles;
-        mbar_wait(&full[s], use & 1, p.error_flag);
-        if (first && win >= 2) mbar_wait(&acc_empty[as], ((win >> 1) - 1) & 1, p.error_flag);
-        tc_fence_after();
+    // =========================================================================== MMA issue (converged warp, one elected lane)
+    // D f32, A / B bf16, both K-major, M = N = 128
+    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t base = smem_u32(smem);
+    for (uint32_t it = 0; it < (uint32_t)my_tiles; it++) {
+      const int s = it & 1;
+      const uint32_t use = it >> 1, win = it / kFlush, as = win & 1;
+      const bool first = (it % kFlush) == 0, last = (it % kFlush) == kFlush - 1 || it + 1 == (uint32_t)my_tiles;
+      mbar_wait(&full[s], use & 1, p.error_flag);
+      if (first && win >= 2) mbar_wait(&acc_empty[as], ((win >> 1) - 1) & 1, p.error_flag);
+      tc_fence_after();
+      if (elect_one()) {
         const uint32_t acc0 = tmem_base + as * 256u, acc1 = acc0 + 128u;
-        const uint32_t bs = base + s * kGradStageBytes, as_ = bs + kStageBytes;
+        const uint32_t b_lo = desc_lo(base + s * kGradStageBytes, 16), a_lo = desc_lo(base + s * kGradStageBytes + kStageBytes, 16);
         bool first1 = true;
 #pragma unroll
         for (int pb = 0; pb < 3; pb++) {
@@ -681,10 +709,9 @@ __global__ void __launch_bounds__(kThreads, 1)
             const bool lead = (pb == 0 && pa == 0);
 #pragma unroll
             for (int ks = 0; ks < 4; ks++) {   // K = 16 columns n per instruction: 32 bytes along the 128-byte rows
-              const uint64_t ad = make_desc(bs + pb * kSliceBytesX + ks * 32, 16, 1024);
-              const uint64_t bd = make_desc(as_ + pa * kSliceBytesX + ks * 32, 16, 1024);
               const uint32_t accumulate = lead ? !(first && ks == 0) : !(first && first1 && ks == 0);
-              umma_bf16(lead ? acc0 : acc1, ad, bd, idesc, accumulate);
+              umma_bf16(lead ? acc0 : acc1, desc_at(b_lo, kDescHi, pb * kSliceBytesX + ks * 32),
+                        desc_at(a_lo, kDescHi, pa * kSliceBytesX + ks * 32), idesc, accumulate);
             }
             if (!lead) first1 = false;
           }
@@ -692,6 +719,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         umma_commit(&empty[s]);
         if (last) umma_commit(&acc_done[as]);
       }
+      __syncwarp();
     }
   } else {
     // =========================================================================== drain: flush windows

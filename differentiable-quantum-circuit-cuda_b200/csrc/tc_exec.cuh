@@ -4,9 +4,10 @@
 // A window whose gates are all unitary kinds runs as ONE dense 64 x 64 block:
 //
 //   forward : W = U_m ... U_1 (host, double) -> bf16 slice image -> k_tc_block_fwd            (2*S of HBM traffic)
-//   reverse : state <- W^dagger state (k_tc_block_fwd), G_W = sum adjoint (x) state (k_tc_block_grad, 2*S read),
-//             adjoint <- W^T adjoint (k_tc_block_fwd)                                          (6*S)
-//             and, once per backward() call, the chain rule from the block gradients G_W to the member gates:
+//   reverse : ONE fused sweep (tc_rev.cuh: k_tc_block_rev, 4*S): state <- W^dagger state, adjoint <- W^T adjoint,
+//             H += adjoint (x) state, and G_W = H conj(W) on the host.  (Option tc_rev = 0 keeps the three-sweep form:
+//             k_tc_block_fwd, k_tc_block_grad, k_tc_block_fwd, 6*S.)
+//             Once per backward() call, the chain rule from the block gradients G_W to the member gates:
 //             with L_k = U_m .. U_{k+1}, R_k = U_{k-1} .. U_1 the gradient of U_k (embedded) is
 //             E_k = L_k^T G_W R_k^T, updated from gate to gate by E_{k+1} = conj(U_{k+1}) E_k U_k^T, and the 4 x 4
 //             (2 x 2, diagonal) reference gradient is its partial trace over the other window qubits --
@@ -18,6 +19,7 @@
 #include <thread>
 
 #include "tc_block.cuh"
+#include "tc_rev.cuh"
 #include "tc_host.hpp"
 #include "tile_kernels.cuh"
 
@@ -69,6 +71,7 @@ inline const char* Circuit::tc_ensure(size_t image_slots, size_t grad_slots) {
   if (!tc.attr_set) {
     QDC_CUDA(cudaFuncSetAttribute(tcb::k_tc_block_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, tcb::kSmemBytes));
     QDC_CUDA(cudaFuncSetAttribute(tcb::k_tc_block_grad, cudaFuncAttributeMaxDynamicSharedMemorySize, tcb::kGradSmemBytes));
+    QDC_CUDA(cudaFuncSetAttribute(tcb::k_tc_block_rev, cudaFuncAttributeMaxDynamicSharedMemorySize, tcb::kRevSmemBytes));
     QDC_CUDA(cudaMalloc((void**)&tc.d_error, sizeof(int)));
     QDC_CUDA(cudaMemset(tc.d_error, 0, sizeof(int)));
     tc.attr_set = true;
@@ -156,8 +159,9 @@ inline const char* Circuit::tc_prepare(const qdc::Step& t, const std::vector<con
   return nullptr;
 }
 
-// form: 0 = W, 1 = W^dagger, 2 = W^T
-inline const char* Circuit::tc_launch_block(cplx_t* buf, const tcb::Params& geo_in, const Mat64& w, int form) {
+// form: 0 = W, 1 = W^dagger, 2 = W^T.  launch = false: only stage the image (geo_out->w_image) for another kernel.
+inline const char* Circuit::tc_launch_block(cplx_t* buf, const tcb::Params& geo_in, const Mat64& w, int form, bool launch,
+                                            tcb::Params* geo_out) {
   TcState& tc = *tc_;
   if (tc.image_used >= tc.image_slots) return qdc_errf("internal: tensor-core image ring exhausted.");
   std::vector<double> flat(64 * 64 * 2);
@@ -177,6 +181,8 @@ inline const char* Circuit::tc_launch_block(cplx_t* buf, const tcb::Params& geo_
   geo.w_image = d;
   geo.error_flag = tc.d_error;
   geo.products = opt_tc_products_;
+  if (geo_out) *geo_out = geo;
+  if (!launch) return nullptr;
   DeviceInfo di;
   QDC_TRY(qdc_device_info(&di));
   const int grid = (int)std::min<uint64_t>(geo.ntiles, (uint64_t)di.sm_count);
@@ -194,7 +200,7 @@ inline const char* Circuit::run_tc_forward(const qdc::Step& t, const std::vector
   tc_block_matrix(pass, w);
   cudaEvent_t pa = nullptr;
   if (prof_.on) pa = prof_.begin(stream_);
-  QDC_TRY(tc_launch_block(state_, geo, w, uncompute ? 1 : 0));
+  QDC_TRY(tc_launch_block(state_, geo, w, uncompute ? 1 : 0, true));
   if (prof_.on) prof_.end(stream_, uncompute ? CAT_UNCOMPUTE : CAT_TC_FWD, pa, 2ull * t.count * bytes());
   stats_.kernel_launches += 1;
   stats_.hbm_passes += 1;
@@ -215,28 +221,40 @@ inline const char* Circuit::run_tc_backward(const qdc::Step& t, const std::vecto
   tc_block_matrix(pass, w);
   cudaEvent_t pa = nullptr;
   if (prof_.on) pa = prof_.begin(stream_);
-  QDC_TRY(tc_launch_block(state_, geo, w, 1));                       // state <- W^dagger state
-  {
-    DeviceInfo di;
-    QDC_TRY(qdc_device_info(&di));
-    const int grid = (int)std::min<uint64_t>(geo.ntiles, (uint64_t)di.sm_count);
+  DeviceInfo di;
+  QDC_TRY(qdc_device_info(&di));
+  const int grid = (int)std::min<uint64_t>(geo.ntiles, (uint64_t)di.sm_count);
+  double* slot = tc.d_grads + (size_t)pass.grad_slot * tcb::kDim * tcb::kDim;
+  QDC_CUDA(cudaMemsetAsync(tc.d_partials, 0, (size_t)grid * tcb::kDim * tcb::kDim * sizeof(float), stream_));
+  pass.from_h = opt_tc_rev_ != 0;
+  if (opt_tc_rev_) {
+    // one sweep: state <- W^dagger state, adjoint <- W^T adjoint, H += adjoint (x) state
+    tcb::RevParams rp;
+    QDC_TRY(tc_launch_block(nullptr, geo, w, 1, false, &rp.geo));
+    rp.partials = tc.d_partials;
+    tcb::k_tc_block_rev<<<grid, tcb::kRevThreads, tcb::kRevSmemBytes, stream_>>>((float2*)state_, (float2*)bwd_, rp);
+    QDC_CUDA(cudaGetLastError());
+    tcb::k_tc_grad_reduce<<<(tcb::kDim * tcb::kDim + 255) / 256, 256, 0, stream_>>>(tc.d_partials, grid, slot, 0);
+    QDC_CUDA(cudaGetLastError());
+    stats_.kernel_launches += 2;
+    stats_.hbm_passes += 2;
+  } else {
+    QDC_TRY(tc_launch_block(state_, geo, w, 1, true));                 // state <- W^dagger state
     tcb::GradParams gpar;
     gpar.geo = geo;
     gpar.geo.error_flag = tc.d_error;
     gpar.geo.w_image = nullptr;
     gpar.geo.products = 6;
     gpar.partials = tc.d_partials;
-    QDC_CUDA(cudaMemsetAsync(tc.d_partials, 0, (size_t)grid * tcb::kDim * tcb::kDim * sizeof(float), stream_));
     tcb::k_tc_block_grad<<<grid, tcb::kThreads, tcb::kGradSmemBytes, stream_>>>((const float2*)state_, (const float2*)bwd_, gpar);
     QDC_CUDA(cudaGetLastError());
-    tcb::k_tc_grad_reduce<<<(tcb::kDim * tcb::kDim + 255) / 256, 256, 0, stream_>>>(
-        tc.d_partials, grid, tc.d_grads + (size_t)pass.grad_slot * tcb::kDim * tcb::kDim, 0);
+    tcb::k_tc_grad_reduce<<<(tcb::kDim * tcb::kDim + 255) / 256, 256, 0, stream_>>>(tc.d_partials, grid, slot, 0);
     QDC_CUDA(cudaGetLastError());
+    QDC_TRY(tc_launch_block(bwd_, geo, w, 2, true));                   // adjoint <- W^T adjoint
+    stats_.kernel_launches += 4;
+    stats_.hbm_passes += 3;
   }
-  QDC_TRY(tc_launch_block(bwd_, geo, w, 2));                         // adjoint <- W^T adjoint
   if (prof_.on) prof_.end(stream_, CAT_TC_BWD, pa, 4ull * t.count * bytes());
-  stats_.kernel_launches += 4;
-  stats_.hbm_passes += 3;
   stats_.algorithmic_bytes += 4ull * t.count * bytes();
   return nullptr;
 }
@@ -259,10 +277,11 @@ inline const char* Circuit::tc_finish_backward() {
       const size_t pi = next.fetch_add(1);
       if (pi >= np) return;
       const TcPass& pass = tc.passes[pi];
-      tc_chain_rule(
-          pass, &P[(size_t)pass.grad_slot * tcb::kDim * tcb::kDim],
-          [&](int k) { return kind_is_var(insts_[pass.gates[k].inst].kind); },
-          [&](int k, const zc* v, int count) { tc.grad_of_inst[pass.gates[k].inst].assign(v, v + count); });
+      const double* pp = &P[(size_t)pass.grad_slot * tcb::kDim * tcb::kDim];
+      auto want = [&](int k) { return kind_is_var(insts_[pass.gates[k].inst].kind); };
+      auto emit = [&](int k, const zc* v, int count) { tc.grad_of_inst[pass.gates[k].inst].assign(v, v + count); };
+      if (pass.from_h) tc_chain_rule_from_h(pass, pp, want, emit);
+      else tc_chain_rule(pass, pp, want, emit);
     }
   };
   unsigned nt = std::thread::hardware_concurrency();

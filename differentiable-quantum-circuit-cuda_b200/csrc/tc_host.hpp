@@ -19,6 +19,7 @@ struct TcGate {
 struct TcPass {
   std::vector<TcGate> gates;   // forward execution order
   int grad_slot = -1;          // slot in d_tcgrad_ (reverse pass with a live adjoint)
+  bool from_h = false;         // the slot holds P' of the fused reverse kernel (tc_chain_rule_from_h), not P
 };
 
 // M <- (g embedded on index bits) * M   (acts on the row index)
@@ -82,15 +83,11 @@ static inline void tc_partial_trace(const Mat64& e, int nq, int b2, int b1, zc* 
   }
 }
 
-// Block gradient -> gate gradients.  P: the 128 x 128 real matrix of k_tc_block_grad (row = real-ified adjoint
-// index, column = real-ified state index, kernel bit order).  `want(k)` says whether gate k needs a gradient;
-// `emit(k, values, count)` receives it in the reference's layout (row-major 2 x 2 / 4 x 4, or the 4 diagonal entries).
+// Block gradient -> gate gradients.  e: G_W[i, j] = sum adjoint_after[i] * state_before[j] (kernel bit order), destroyed.
+// `want(k)` says whether gate k needs a gradient; `emit(k, values, count)` receives it in the reference's layout
+// (row-major 2 x 2 / 4 x 4, or the 4 diagonal entries).
 template <class Want, class Emit>
-static inline void tc_chain_rule(const TcPass& pass, const double* p, Want want, Emit emit) {
-  Mat64 e(64 * 64);
-  for (int i = 0; i < 64; i++)
-    for (int j = 0; j < 64; j++)
-      e[i * 64 + j] = zc(p[i * 128 + j] - p[(64 + i) * 128 + 64 + j], p[i * 128 + 64 + j] + p[(64 + i) * 128 + j]);
+static inline void tc_chain_rule_g(const TcPass& pass, Mat64& e, Want want, Emit emit) {
   const int m = (int)pass.gates.size();
   zc tmp[16];
   // E_1 = U_2^T ( ... (U_m^T G_W))
@@ -121,6 +118,38 @@ static inline void tc_chain_rule(const TcPass& pass, const double* p, Want want,
       tc_apply_cols(e, g.m, g.nq, g.b2, g.b1);       // ... E U_k^T
     }
   }
+}
+
+// P: the 128 x 128 real matrix of k_tc_block_grad (row = real-ified adjoint index, column = real-ified index of the
+// state BEFORE the block, kernel bit order).
+template <class Want, class Emit>
+static inline void tc_chain_rule(const TcPass& pass, const double* p, Want want, Emit emit) {
+  Mat64 e(64 * 64);
+  for (int i = 0; i < 64; i++)
+    for (int j = 0; j < 64; j++)
+      e[i * 64 + j] = zc(p[i * 128 + j] - p[(64 + i) * 128 + 64 + j], p[i * 128 + 64 + j] + p[(64 + i) * 128 + j]);
+  tc_chain_rule_g(pass, e, want, emit);
+}
+
+// P': the 128 x 128 real matrix of the fused reverse kernel k_tc_block_rev (tc_rev.cuh): row = real-ified index of the
+// CONJUGATED adjoint after the block, column = real-ified index of the state AFTER the block (both as loaded), i.e.
+// H[i, k] = sum adjoint[i] * state_after[k] has Re = P'[i, k] + P'[64 + i, 64 + k], Im = P'[i, 64 + k] - P'[64 + i, k].
+// With state_before = W^dagger state_after:  G_W = H conj(W) = H conj(U_m) conj(U_{m-1}) ... conj(U_1).
+template <class Want, class Emit>
+static inline void tc_chain_rule_from_h(const TcPass& pass, const double* p, Want want, Emit emit) {
+  Mat64 e(64 * 64);
+  for (int i = 0; i < 64; i++)
+    for (int k = 0; k < 64; k++)
+      e[i * 64 + k] = zc(p[i * 128 + k] + p[(64 + i) * 128 + 64 + k], p[i * 128 + 64 + k] - p[(64 + i) * 128 + k]);
+  zc tmp[16];
+  for (int k = (int)pass.gates.size() - 1; k >= 0; k--) {
+    const TcGate& g = pass.gates[k];
+    const int K = g.nq == 1 ? 2 : 4;
+    for (int r = 0; r < K; r++)   // M conj(U) = M (U^dagger)^T
+      for (int c = 0; c < K; c++) tmp[r * K + c] = std::conj(g.m[c * K + r]);
+    tc_apply_cols(e, tmp, g.nq, g.b2, g.b1);
+  }
+  tc_chain_rule_g(pass, e, want, emit);
 }
 
 static inline void tc_block_matrix(const TcPass& pass, Mat64& w) {

@@ -63,6 +63,28 @@ int main() {
     std::vector<std::vector<zc>> got(m);
     tc_chain_rule(pass, P.data(), [](int) { return true; },
                   [&](int k, const zc* v, int count) { got[k].assign(v, v + count); });
+    // the fused reverse kernel's form: P'[mu, nu] = sum_r conj(B)~[mu, r] X~[nu, r] with X = W A the state AFTER the block
+    {
+      Mat64 X(A);
+      for (const TcGate& g : pass.gates) tc_apply_rows(X, g.m, g.nq, g.b2, g.b1);
+      std::vector<double> Pp(128 * 128, 0.0);
+      for (int mu = 0; mu < 128; mu++)
+        for (int nu = 0; nu < 128; nu++) {
+          double s = 0;
+          for (int r = 0; r < 64; r++) {
+            const zc b = std::conj(B[(mu & 63) * 64 + r]), x = X[(nu & 63) * 64 + r];
+            s += (mu < 64 ? b.real() : b.imag()) * (nu < 64 ? x.real() : x.imag());
+          }
+          Pp[mu * 128 + nu] = s;
+        }
+      std::vector<std::vector<zc>> got_h(m);
+      tc_chain_rule_from_h(pass, Pp.data(), [](int) { return true; },
+                           [&](int k, const zc* v, int count) { got_h[k].assign(v, v + count); });
+      for (int k = 0; k < m; k++) {
+        if (got_h[k].size() != got[k].size()) { printf("FAIL: from_h gradient length\n"); return 1; }
+        for (size_t i = 0; i < got[k].size(); i++) worst = std::max(worst, std::abs(got_h[k][i] - got[k][i]) / 64.0);
+      }
+    }
     // the block matrix is the ordered product of the gates
     {
       Mat64 w, seq(A);

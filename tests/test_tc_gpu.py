@@ -39,10 +39,11 @@ def _brickwork(n, depth, options):
     return dens, grads, prof_f, prof_b, back
 
 
-@pytest.mark.parametrize("n,depth", [(16, 10), (22, 12)])
-def test_tc_brickwork_equals_per_gate_executor(pkg, n, depth):
+@pytest.mark.parametrize("n,depth,extra", [(16, 10, ()), (22, 12, ()), (16, 10, (("tc_rev", 0),)), (20, 12, (("tc_products", 6),))])
+def test_tc_brickwork_equals_per_gate_executor(pkg, n, depth, extra):
+    """Default: the fused one-sweep reverse step (tc_rev.cuh); tc_rev = 0: the three-sweep form; tc_products = 6."""
     dens0, grads0, _, _, _ = _brickwork(n, depth, (("fuse", 0),))
-    dens, grads, pf, pb, back = _brickwork(n, depth, (("tc", 1),))
+    dens, grads, pf, pb, back = _brickwork(n, depth, (("tc", 1),) + tuple(extra))
     assert pf.get("tc_fwd", {}).get("launches", 0) > 0 and pb.get("tc_bwd", {}).get("launches", 0) > 0, \
         "the tensor-core blocks must be the ones that ran"
     assert _max_rel(dens, dens0) < TOL and _max_rel(grads, grads0) < TOL, (_max_rel(dens, dens0), _max_rel(grads, grads0))
