@@ -220,10 +220,12 @@ class Circuit {
   int opt_tile_strategy_ = 2;  // scheduler.hpp: 2 window growth with look-ahead, 1 window growth, 0 first-fit tiling
   int opt_batch_dens_ = 1;    // 1: densities / density seeds of one program point share tiled sweeps (tile_dens_kernels.cuh)
   int opt_soa_ = 1;           // f32 tile kernels: 1 pair-lane shared-memory layout (tile_soa_kernels.cuh), 0 interleaved
-  // f32: 1 = windows of <= 6 qubits on positions >= 3 run as dense 64 x 64 blocks on the tensor cores
-  // (tc_exec.cuh / tc_block.cuh); the scheduler then grows 6-position windows
-  int opt_tc_ = 0;
-  int opt_tc_products_ = 8;   // bf16 slice products per block (tc_block.cuh)
+  // f32: 1 = windows of <= 6 qubits run as dense 64 x 64 blocks on the tensor cores (tc_exec.cuh / tc_block.cuh /
+  // tc_rev.cuh); the scheduler then grows 6-position windows.  -1 (default): on for shards of >= 2^26 amplitudes,
+  // where a block's sweep outweighs its host work (64 x 64 products, slice image, 96 KiB upload); 0: FP32-pipe tile
+  // kernels only.
+  int opt_tc_ = -1;
+  int opt_tc_products_ = 6;   // bf16 slice products per block (tc_block.cuh): 6 = orders 0..2; 8 adds order 3 (2^-27 relative)
   int opt_tc_rev_ = 1;        // reverse step of a block: 1 one fused sweep (tc_rev.cuh, 4*S), 0 three sweeps (6*S)
   TcState* tc_ = nullptr;
   int opt_tile_bits_ = 0;  // 0: default for the precision
@@ -610,7 +612,8 @@ class Circuit {
 
   bool tc_active() const {
 #ifndef QDC_F64
-    return opt_tc_ && opt_fuse_ && n_loc_ >= 14;
+    const bool on = opt_tc_ < 0 ? n_loc_ >= 26 : opt_tc_ != 0;
+    return on && opt_fuse_ && n_loc_ >= 14;
 #else
     return false;
 #endif

@@ -140,7 +140,7 @@ QDC_EXPORT const char* qdc_circuit_set_option(qdc_circuit* c, const char* key, l
   else if (strcmp(key, "peer") == 0) c->impl.opt_peer_ = (int)value;  // 0: force the NCCL send/recv exchange
   else if (strcmp(key, "tc") == 0) {   // f32: tensor-core fused 6-qubit blocks (tc_exec.cuh)
 #ifdef QDC_F64
-    if (value) return qdc_errf("option \"tc\" exists in the f32 build only.");
+    if (value > 0) return qdc_errf("option \"tc\" exists in the f32 build only.");
 #endif
     c->impl.opt_tc_ = (int)value;
   } else if (strcmp(key, "tc_products") == 0) {

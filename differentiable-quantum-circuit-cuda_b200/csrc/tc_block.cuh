@@ -64,7 +64,12 @@ constexpr int kFillThreads = kFillWarps * 32, kDrainThreads = kDrainWarps * 32;
 constexpr int kThreads = kFillThreads + 32 + kDrainThreads;   // 416
 constexpr int kTmemCols = 512;     // W slices: 3 x 64 columns (bf16 pairs); accumulators: columns 256.. : 2 stages x (A0, A1) x 64
 constexpr int kTmemAcc = 256;
-constexpr int kPrefetch = 5;        // tiles of L2 prefetch distance per CTA
+#ifndef TC_PREFETCH
+#define TC_PREFETCH 0
+#endif
+// tiles of L2 prefetch distance per CTA: 0 = off (default; with the fill's register pipeline a whole tile period ahead of
+// its use, the prefetch instructions only cost issue cycles -- profiles/r2_tc_rev_bench_v3.txt)
+constexpr int kPrefetch = TC_PREFETCH;
 
 // Software bit deposit: tile number -> amplitude base (same role as TileGeo::tile)
 struct Deposit {
@@ -92,10 +97,25 @@ struct Params {
   int elem_off[8];       // amplitude offset of element e of an item (deposit of e into the positions of n0..n2)
   int fast;
   Deposit tile;          // tile number -> amplitude base over the other n - 12 positions
+  uint64_t tile_mask;    // the 12 positions of the tile as an index mask (TileWalk)
   uint64_t ntiles;
   const uint32_t* w_image; // 96 KiB: [slice][row mu][64 words], word k2 = (bf16 of column 2 k2) | (bf16 of column 2 k2 + 1) << 16
   int* error_flag;         // set to 1 by a watchdog if a barrier wait times out
   int products;            // 8: all slice products but p2 * p2;  6: also without p1 * p2, p2 * p1 (2^-24 relative each)
+};
+
+// Amplitude base of a CTA's tiles, advanced by a fixed stride WITHOUT the software bit deposit (a loop of 64-bit
+// shifts over constant-bank tables that every thread paid several times per tile: 14 % of the warp stall samples of
+// profiles/r2_tc_rev_28q_v2_ncu.txt).  With F = the tile's own positions, which the tile counter skips,
+// deposit(a + b) = ((deposit(a) | F) + deposit(b)) & ~F: the carries run through the filled positions.
+struct TileWalk {
+  uint64_t cur, step, skip;
+  __device__ __forceinline__ void init(const Params& p, uint64_t first, uint64_t stride) {
+    cur = p.tile(first);
+    step = p.tile(stride);
+    skip = p.tile_mask;
+  }
+  __device__ __forceinline__ void advance() { cur = ((cur | skip) + step) & ~skip; }
 };
 
 // ------------------------------------------------------------------ byte images (host and device)
@@ -288,6 +308,33 @@ __device__ __forceinline__ void store_item(float2* __restrict__ dst, const Param
   }
 }
 
+// magic numbers of the 9-bit slicing (grids 2^(E - 8), 2^(E - 17), 2^(E - 26), 2^E > max), see k_tc_block_fwd
+__device__ __forceinline__ void magic_of(uint32_t bexp, float& m0, float& m1, float& m2) {
+  bexp = bexp < 32u ? 32u : (bexp > 230u ? 230u : bexp);
+  const uint32_t m0b = ((bexp + 16u) << 23) | 0x400000u;
+  m0 = __uint_as_float(m0b);
+  m1 = __uint_as_float(m0b - (9u << 23));
+  m2 = __uint_as_float(m0b - (18u << 23));
+}
+
+// Slicing grid of a fill warp WITHOUT a CTA-wide barrier: the exponent of the largest |value| this warp holds (one REDUX),
+// raised to the running maximum the warps of the CTA publish in shared memory (monotone, read without synchronisation).
+// The slices are ordinary f32 / bf16 VALUES, so a warp that is briefly one binade ahead of the others costs nothing but
+// the slack of the exactness bound (K = 128 leading products of <= 2^16 grid units leave one binade below 2^24), and the
+// absolute quantisation error stays 2^-27 of the largest amplitude this CTA has seen.
+__device__ __forceinline__ uint32_t warp_grid_exp(const float4 (&v)[2][4], uint32_t* e_shared, uint32_t e_run, int lane) {
+  float mx = 0.f;
+#pragma unroll
+  for (int it = 0; it < 2; it++)
+#pragma unroll
+    for (int h = 0; h < 4; h++)
+      mx = fmaxf(fmaxf(mx, fmaxf(fabsf(v[it][h].x), fabsf(v[it][h].y))), fmaxf(fabsf(v[it][h].z), fabsf(v[it][h].w)));
+  const uint32_t e = __reduce_max_sync(0xffffffffu, (__float_as_uint(mx) >> 23) & 0xffu);
+  const uint32_t es = *(volatile uint32_t*)e_shared;
+  if (e > es && lane == 0) atomicMax(e_shared, e);
+  return max(e_run, max(e, es));
+}
+
 // ------------------------------------------------------------------------------------ the kernel
 // state: 2^n interleaved (re, im) f32 pairs, updated in place: every group of 64 amplitudes over the block
 // qubits is multiplied by W.
@@ -311,12 +358,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_block_fwd(float2* __restrict
   uint64_t* mma_done = bars + 2 * kStages;     // [kStages]    MMA -> drain   (tcgen05.commit)
   uint64_t* tmem_empty = bars + 3 * kStages;   // [kAccStages] drain -> MMA   (128 arrivals)
   uint32_t* tmem_slot = (uint32_t*)(bars + 3 * kStages + kAccStages);
-  float* sm_max = (float*)(tmem_slot + 2);     // [2][8] warp maxima of the fill group (double-buffered by tile parity)
+  uint32_t* e_shared = tmem_slot + 2;          // running maximum exponent of the fill warps (warp_grid_exp)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   // ---- one-time setup
   if (threadIdx.x == 0) {
+    *e_shared = 0;
     for (int s = 0; s < kStages; s++) {
       mbar_init(&full[s], kFillThreads);
       mbar_init(&empty[s], kDrainThreads);
@@ -362,22 +410,26 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_block_fwd(float2* __restrict
     const int t = threadIdx.x;
     ItemAddr<2, kFillThreads> ia;
     ia.init(p, t);
+    TileWalk wl, wp;   // base of the tile whose loads are issued next / of the tile prefetched into L2 next
+    wl.init(p, blockIdx.x, gridDim.x);
+    wp = wl;
     // L2 prefetch of the first tiles of this CTA
     for (int k = 0; k < kPrefetch; k++) {
       const uint64_t tl = blockIdx.x + (uint64_t)k * gridDim.x;
       if (tl < p.ntiles) {
-        const float2* src = state + p.tile(tl);
+        const float2* src = state + wp.cur;
 #pragma unroll
         for (int it = 0; it < 2; it++) prefetch_item(src + ia.goff[it], p);
       }
+      wp.advance();
     }
-    uint32_t it_count = 0;
+    uint32_t it_count = 0, e_run = 0;
     // Software pipeline over registers: the loads of the NEXT tile are issued as soon as this tile's slices have been
     // taken, so that a whole tile (32 KiB, ~1500 cycles at this SM's share of the HBM bandwidth) is in flight while
     // the fill fences, waits for its stage and reduces the next maximum.  The L2 prefetch runs kPrefetch tiles ahead.
     float4 v[2][4];
     if ((uint64_t)blockIdx.x < p.ntiles) {
-      const float2* src = state + p.tile(blockIdx.x);
+      const float2* src = state + wl.cur;
 #pragma unroll
       for (int it = 0; it < 2; it++) load_item(src + ia.goff[it], p, v[it]);
     }
@@ -385,28 +437,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_block_fwd(float2* __restrict
       const int s = it_count % kStages;
       const uint32_t use = it_count / kStages;
       if (tile + (uint64_t)kPrefetch * gridDim.x < p.ntiles) {
-        const float2* src = state + p.tile(tile + (uint64_t)kPrefetch * gridDim.x);
+        const float2* src = state + wp.cur;
 #pragma unroll
         for (int it = 0; it < 2; it++) prefetch_item(src + ia.goff[it], p);
       }
-      float mx = 0.f;
-#pragma unroll
-      for (int it = 0; it < 2; it++)
-#pragma unroll
-        for (int h = 0; h < 4; h++)
-          mx = fmaxf(fmaxf(mx, fmaxf(fabsf(v[it][h].x), fabsf(v[it][h].y))), fmaxf(fabsf(v[it][h].z), fabsf(v[it][h].w)));
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-      float* mxbuf = sm_max + (it_count & 1) * 8;
-      if (lane == 0) mxbuf[warp] = mx;
-      named_bar(1, kFillThreads);    // (the buffer of the tile before last is free again: one barrier per tile suffices)
-      mx = fmaxf(fmaxf(fmaxf(mxbuf[0], mxbuf[1]), fmaxf(mxbuf[2], mxbuf[3])), fmaxf(fmaxf(mxbuf[4], mxbuf[5]), fmaxf(mxbuf[6], mxbuf[7])));
+      wp.advance();
       // 9-bit slices: grids 2^(E - 8), 2^(E - 17), 2^(E - 26) with 2^E > max: |k_i| <= 256 is still exact in bf16
       // (8 significant bits) and the leading products stay exact: 128 * 2^16 = 2^23 < 2^24
-      uint32_t bexp = (__float_as_uint(mx) >> 23) & 0xffu;
-      bexp = bexp < 32u ? 32u : (bexp > 230u ? 230u : bexp);
-      const uint32_t m0b = ((bexp + 16u) << 23) | 0x400000u;   // 1.5 * 2^(E + 15), 2^E > max
-      const float m0 = __uint_as_float(m0b), m1 = __uint_as_float(m0b - (9u << 23)), m2 = __uint_as_float(m0b - (18u << 23));
+      e_run = warp_grid_exp(v, e_shared, e_run, lane);
+      float m0, m1, m2;
+      magic_of(e_run, m0, m1, m2);
       if (use > 0) mbar_wait(&empty[s], (use - 1) & 1, p.error_flag);
       uint8_t* stage = sm_x + s * kStageBytes;
 #pragma unroll
@@ -431,12 +471,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_block_fwd(float2* __restrict
               make_uint4(pack_hi16(q2[0], q2[1]), pack_hi16(q2[2], q2[3]), pack_hi16(q2[4], q2[5]), pack_hi16(q2[6], q2[7]));
         }
       }
+      wl.advance();
       if (tile + gridDim.x < p.ntiles) {
-        const float2* src = state + p.tile(tile + gridDim.x);
+        const float2* src = state + wl.cur;
 #pragma unroll
         for (int it = 0; it < 2; it++) load_item(src + ia.goff[it], p, v[it]);
       }
-      fence_async_smem();
+      // (the proxy fence is executed by the MMA warp after it has acquired `full`: here it would wait for the loads
+      // that this thread has just issued)
       mbar_arrive(&full[s]);
     }
   } else if (warp == kFillWarps) {
@@ -451,6 +493,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_block_fwd(float2* __restrict
       const int s = it_count % kStages, as = it_count % kAccStages;
       const uint32_t use = it_count / kStages, ause = it_count / kAccStages;
       mbar_wait(&full[s], use & 1, p.error_flag);
+      fence_async_smem();   // generic-proxy stores of the fill warps (acquired through `full`) -> async-proxy reads of the MMAs
       if (ause > 0) mbar_wait(&tmem_empty[as], (ause - 1) & 1, p.error_flag);
       tc_fence_after();
       if (elect_one()) {
@@ -485,8 +528,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_block_fwd(float2* __restrict
     const int mu = q4 * 32 + lane;           // output row (c', i)
     ItemAddr<4, kDrainThreads> ia;
     ia.init(p, t128);
+    TileWalk wd;
+    wd.init(p, blockIdx.x, gridDim.x);
     uint32_t it_count = 0;
-    for (uint64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, it_count++) {
+    for (uint64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, it_count++, wd.advance()) {
       const int s = it_count % kStages, as = it_count % kAccStages;
       const uint32_t use = it_count / kStages;
       mbar_wait(&mma_done[s], use & 1, p.error_flag);
@@ -509,19 +554,26 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_block_fwd(float2* __restrict
       tc_fence_before();
       mbar_arrive(&tmem_empty[as]);               // the accumulators of this stage may be overwritten
       named_bar(2, kDrainThreads);
-      float2* dst = state + p.tile(tile);
+      float2* dst = state + wd.cur;
+      // staging -> registers; the stage is free for the fill as soon as every drain thread has read its rows -- the
+      // global stores follow from the registers
+      float4 r[4][4];
 #pragma unroll
       for (int it = 0; it < 4; it++) {
-        const float4 r0 = *(const float4*)(stage + ia.soff[it]);
-        const float4 r1 = *(const float4*)(stage + kSliceBytesX + ia.soff[it]);
-        const float4 i0 = *(const float4*)(stage + ia.soff[it] + 8192u);
-        const float4 i1 = *(const float4*)(stage + kSliceBytesX + ia.soff[it] + 8192u);
+        r[it][0] = *(const float4*)(stage + ia.soff[it]);
+        r[it][1] = *(const float4*)(stage + kSliceBytesX + ia.soff[it]);
+        r[it][2] = *(const float4*)(stage + ia.soff[it] + 8192u);
+        r[it][3] = *(const float4*)(stage + kSliceBytesX + ia.soff[it] + 8192u);
+      }
+      named_bar(2, kDrainThreads);
+      mbar_arrive(&empty[s]);
+#pragma unroll
+      for (int it = 0; it < 4; it++) {
+        const float4 r0 = r[it][0], r1 = r[it][1], i0 = r[it][2], i1 = r[it][3];
         const float4 o[4] = {make_float4(r0.x, i0.x, r0.y, i0.y), make_float4(r0.z, i0.z, r0.w, i0.w),
                              make_float4(r1.x, i1.x, r1.y, i1.y), make_float4(r1.z, i1.z, r1.w, i1.w)};
         store_item(dst + ia.goff[it], p, o);
       }
-      named_bar(2, kDrainThreads);                // every drain thread has read its staging rows
-      mbar_arrive(&empty[s]);
     }
   }
 
@@ -552,6 +604,7 @@ constexpr int kGradStageBytes = 2 * kStageBytes;   // b slices, then a slices: 9
 constexpr int kGradStages = 2;
 constexpr int kGradSmemBytes = kGradStages * kGradStageBytes + 1024 + 512;
 constexpr int kFlush = 4;
+constexpr int kGradPrefetch = 5;   // tiles of L2 prefetch distance (this kernel loads a tile at the start of its iteration)
 
 struct GradParams {
   Params geo;          // pos / j_of / n_of / tile / ntiles / error_flag (w_image, products unused)
@@ -597,15 +650,6 @@ __device__ __forceinline__ float tile_max8(const float4 (&v)[2][4], float* mxbuf
   if (lane == 0) mxbuf[warp] = mx;
   named_bar(bar_id, kFillThreads);
   return fmaxf(fmaxf(fmaxf(mxbuf[0], mxbuf[1]), fmaxf(mxbuf[2], mxbuf[3])), fmaxf(fmaxf(mxbuf[4], mxbuf[5]), fmaxf(mxbuf[6], mxbuf[7])));
-}
-
-// magic numbers of the 9-bit slicing (grids 2^(E - 8), 2^(E - 17), 2^(E - 26), 2^E > max), see k_tc_block_fwd
-__device__ __forceinline__ void magic_of(uint32_t bexp, float& m0, float& m1, float& m2) {
-  bexp = bexp < 32u ? 32u : (bexp > 230u ? 230u : bexp);
-  const uint32_t m0b = ((bexp + 16u) << 23) | 0x400000u;
-  m0 = __uint_as_float(m0b);
-  m1 = __uint_as_float(m0b - (9u << 23));
-  m2 = __uint_as_float(m0b - (18u << 23));
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -660,7 +704,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         prefetch_item(b_state + base + ia.goff[it], p);
       }
     };
-    for (int k = 0; k < kPrefetch; k++)
+    for (int k = 0; k < kGradPrefetch; k++)
       if (blockIdx.x + (uint64_t)k * gridDim.x < p.ntiles) prefetch(blockIdx.x + (uint64_t)k * gridDim.x);
     uint32_t e_run_a = 0, e_run_b = 0;
     uint32_t it_count = 0;
@@ -669,9 +713,9 @@ __global__ void __launch_bounds__(kThreads, 1)
       const uint32_t use = it_count >> 1;
       uint8_t* stage = smem + s * kGradStageBytes;
       float4 vb[2][4], va[2][4];
-      load(b_state, tile, vb);      // out of L2 (prefetched kPrefetch tiles ago); nothing in flight across the fence below
+      load(b_state, tile, vb);      // out of L2 (prefetched kGradPrefetch tiles ago)
       load(a_state, tile, va);
-      if (tile + (uint64_t)kPrefetch * gridDim.x < p.ntiles) prefetch(tile + (uint64_t)kPrefetch * gridDim.x);
+      if (tile + (uint64_t)kGradPrefetch * gridDim.x < p.ntiles) prefetch(tile + (uint64_t)kGradPrefetch * gridDim.x);
       float mx = tile_max8(vb, sm_max + ((it_count & 1) * 2 + 0) * 8, warp, lane, 1);
       e_run_b = max(e_run_b, (__float_as_uint(mx) >> 23) & 0xffu);
       float m0, m1, m2;
@@ -893,6 +937,8 @@ inline const char* make_params(const int* block, int n_qubits, Params* p, int* w
     p->tile.nseg++;
     i = j;
   }
+  p->tile_mask = 0;
+  for (int t = 0; t < kTileBits; t++) p->tile_mask |= 1ull << bits[t];
   p->ntiles = 1ull << (n_qubits - kTileBits);
   return nullptr;
 }

@@ -57,7 +57,7 @@ inline void Circuit::release_tc() {
 
 // Is this TILE step a tensor-core block?  (decided from the plan and the instruction kinds only)
 inline bool Circuit::tc_step_ok(const qdc::Step& t) const {
-  if (!opt_tc_ || n_loc_ < 14 || t.tb_count > tcb::kBlockQubits || t.count < 2) return false;
+  if (!tc_active() || t.tb_count > tcb::kBlockQubits || t.count < 2) return false;
   for (int k = 0; k < t.count; k++)
     if (kind_is_nonu(insts_[plan_.tile_steps[t.first + k].inst].kind)) return false;
   return true;
@@ -232,6 +232,7 @@ inline const char* Circuit::run_tc_backward(const qdc::Step& t, const std::vecto
     tcb::RevParams rp;
     QDC_TRY(tc_launch_block(nullptr, geo, w, 1, false, &rp.geo));
     rp.partials = tc.d_partials;
+    rp.h_products = 6;
     tcb::k_tc_block_rev<<<grid, tcb::kRevThreads, tcb::kRevSmemBytes, stream_>>>((float2*)state_, (float2*)bwd_, rp);
     QDC_CUDA(cudaGetLastError());
     tcb::k_tc_grad_reduce<<<(tcb::kDim * tcb::kDim + 255) / 256, 256, 0, stream_>>>(tc.d_partials, grid, slot, 0);

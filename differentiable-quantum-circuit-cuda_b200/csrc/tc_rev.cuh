@@ -15,17 +15,23 @@
 //
 // Exact 9-bit bf16 slices and the (A0 exact | A1 lower order) accumulator pairs are those of tc_block.cuh.
 //
-// Tensor memory (512 columns): W slices 0, 1 (2 x 64) | H: A0, A1 (2 x 128) | block accumulator: A0, A1 (2 x 64).
-// The third W slice (one product, w2 * x0) is the A operand of its MMAs from shared memory.
-// Shared memory: 2 stages x (X slices 48 KiB + conj(Y) slices 48 KiB) + W slice 2 (32 KiB) = 224 KiB.
+// Tensor memory (512 columns): W slices (3 x 64) | H (128) | block accumulator: A0, A1 (2 x 64).
+// H is ONE accumulator for all its slice products: its truncation bias (~1e-8 per accumulation, a window of kFlush
+// tiles = 96 accumulations) is a relative error of < 1e-6 of a gradient entry, once -- unlike the state and the adjoint,
+// which pass through ~70 blocks and keep the exact (A0 | A1) pair.  That leaves room for all three W slices in tensor
+// memory: every MMA operand read from shared memory shares the L1 data pipe with the fill / drain traffic, which is
+// what bounds this kernel (profiles/r2_tc_rev_28q_v2_ncu.txt: tensor operand wavefronts 41 % + LSU 37 % of the pipe).
+// Shared memory: 2 stages x (X slices 48 KiB + conj(Y) slices 48 KiB) + 32 KiB of output staging = 224 KiB.  The
+// staging buffer is the drain's own, so a stage goes back to the fill the moment its last MMA has completed
+// (tcgen05.commit arrives on the barriers the fill waits on): the stage cycle is fill + MMA, not fill + MMA + drain.
 //
 // Warp roles (416 threads, one CTA per SM, persistent over tiles):
 //   warps 0-7  fill  : HBM (L2-prefetched) -> registers -> running tile maxima -> slices of X and conj(Y) -> `full`
-//   warp  8    MMA   : per tile  H_a | X' -> A | H_b -> B | Y' -> C   (H split in two so that the drain's tcgen05.ld of
-//                      the single block accumulator pair always has tensor work to hide behind)
-//   warps 9-12 drain : A: X' accumulators -> registers (`acc_empty`), B: staged through the dead X slices -> state;
-//                      C: Y' likewise through the dead conj(Y) slices, imaginary part negated -> adjoint; `empty`.
-//                      Every kFlush tiles: H accumulators -> red.global.add into the CTA's private partial.
+//   warp  8    MMA   : one elected lane; per tile  H_a | X' -> A | H_b -> B | Y' -> C   (H split in two so that the
+//                      drain's tcgen05.ld of the single block accumulator pair always has tensor work to hide behind)
+//   warps 9-12 drain : A: X' accumulators -> registers (`acc_empty`) -> staging -> registers -> state;
+//                      C: Y' likewise, imaginary part negated -> adjoint.
+//                      Every kFlush tiles: H accumulator -> red.global.add into the CTA's private partial.
 #pragma once
 #include "tc_block.cuh"
 
@@ -33,15 +39,21 @@ namespace tcb {
 
 constexpr int kRevStageBytes = 2 * kStageBytes;                       // 96 KiB
 constexpr int kRevStages = 2;
-constexpr int kRevW2Off = kRevStages * kRevStageBytes;                // 192 KiB
-constexpr int kRevBarOff = kRevW2Off + kSliceBytesW;                  // 224 KiB
+constexpr int kRevOutOff = kRevStages * kRevStageBytes;               // 192 KiB: output staging, 2 x 16 KiB
+constexpr int kRevBarOff = kRevOutOff + 2 * kSliceBytesX;             // 224 KiB
 constexpr int kRevSmemBytes = kRevBarOff + 1024 /*alignment slack*/ + 512 /*barriers*/;
 constexpr int kRevThreads = kFillThreads + 32 + kDrainThreads;        // 416
-constexpr uint32_t kRevTmH0 = 128, kRevTmH1 = 256, kRevTmA0 = 384, kRevTmA1 = 448;
+#ifndef TC_REV_PREFETCH
+#define TC_REV_PREFETCH 0
+#endif
+constexpr int kRevPrefetch = TC_REV_PREFETCH;
+constexpr uint32_t kRevTmH = 192, kRevTmA0 = 320, kRevTmA1 = 384;
 
 struct RevParams {
   Params geo;          // w_image = image of W^dagger (make_w_image); products: 8 or 6
   float* partials;     // [gridDim.x][128][128], zero on entry; row = real-ified conj(adjoint) index, column = state index
+  int h_products;      // slice products of H: 6 (orders 0..2, 2^-27 per term).  3 (orders 0, 1) is a microbenchmark switch
+                       // only: 2^-18 per term is 6e-5 of the largest entry of an incoherent sum (r2_tc_rev_bench_v6.txt)
 #ifdef TC_REV_TRACE
   long long* trace;    // [8 tiles][32 slots] clock64 stamps of CTA 0, tiles 8..15 (profiles/microbench/tc_rev_bench.cu)
 #endif
@@ -107,24 +119,23 @@ __global__ void __launch_bounds__(kRevThreads, 1)
   const Params& p = rp.geo;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* sm_w2 = smem + kRevW2Off;
   uint64_t* bars = (uint64_t*)(smem + kRevBarOff);
   uint64_t* full = bars;             // [2] fill -> MMA           (256 arrivals)
-  uint64_t* empty = bars + 2;        // [2] drain -> fill         (128 arrivals)
+  uint8_t* sm_out = smem + kRevOutOff;
   uint64_t* bar_a = bars + 4;        // [2] MMA -> drain: X' accumulators complete
-  uint64_t* bar_b = bars + 6;        // [2] MMA -> drain: every MMA reading the X slices of the stage has completed
-  uint64_t* bar_c = bars + 8;        // [2] MMA -> drain: Y' accumulators complete, the stage is no longer read
+  uint64_t* bar_b = bars + 6;        // [2] MMA -> fill: every MMA reading the X slices of the stage has completed
+  uint64_t* bar_c = bars + 8;        // [2] MMA -> drain, fill: Y' accumulators complete, the stage is no longer read
   uint64_t* acc_empty = bars + 10;   // drain -> MMA: block accumulators are in registers (twice per tile)
   uint64_t* h_done = bars + 11;      // MMA -> drain: the H window is complete
   uint64_t* h_empty = bars + 12;     // drain -> MMA: H accumulators have been flushed
   uint32_t* tmem_slot = (uint32_t*)(bars + 13);
-  float* sm_max = (float*)(tmem_slot + 2);   // [2 tile parity][2 x / y][8 warps]
+  uint32_t* e_shared = tmem_slot + 2;        // [2] running maximum exponents of state / adjoint (warp_grid_exp)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
+    e_shared[0] = e_shared[1] = 0;
     for (int s = 0; s < 2; s++) {
       mbar_init(&full[s], kFillThreads);
-      mbar_init(&empty[s], kDrainThreads);
       mbar_init(&bar_a[s], 1);
       mbar_init(&bar_b[s], 1);
       mbar_init(&bar_c[s], 1);
@@ -138,24 +149,16 @@ __global__ void __launch_bounds__(kRevThreads, 1)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
-  // W slice 2 -> shared memory as a K-major SWIZZLE_128B A operand: two K blocks of 64 (128-byte rows), 128 rows.
-  // The global image row holds 64 words = 16 chunks of 8 consecutive k.
-  for (int idx = threadIdx.x; idx < kDim * 16; idx += kRevThreads) {
-    const int m = idx >> 4, ch = idx & 15;
-    const uint4 t = __ldg((const uint4*)(p.w_image + ((size_t)2 * kDim + m) * 64) + ch);
-    *(uint4*)(sm_w2 + (ch >> 3) * 16384 + (m >> 3) * 1024 + (m & 7) * 128 + (((ch ^ m) & 7) << 4)) = t;
-  }
-  fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (warp > kFillWarps) {
-    // W slices 0, 1 -> tensor memory: lane = row mu, column = pair of bf16 along K (64 columns per slice)
+    // W slices -> tensor memory: lane = row mu, column = pair of bf16 along K (64 columns per slice)
     const int q4 = warp & 3, mu = q4 * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q4 * 32) << 16);
 #pragma unroll 1
-    for (int sl = 0; sl < 2; sl++) {
+    for (int sl = 0; sl < kSlices; sl++) {
 #pragma unroll
       for (int half = 0; half < 2; half++) {
         const uint4* src = (const uint4*)(p.w_image + ((size_t)sl * kDim + mu) * 64 + half * 32);
@@ -181,21 +184,27 @@ __global__ void __launch_bounds__(kRevThreads, 1)
     const int t = threadIdx.x;
     ItemAddr<2, kFillThreads> ia;
     ia.init(p, t);
-    auto load = [&](const float2* base, uint64_t tile, float4 (&v)[2][4]) {
-      const float2* src = base + p.tile(tile);
+    auto load = [&](const float2* base, uint64_t tbase, float4 (&v)[2][4]) {
+      const float2* src = base + tbase;
 #pragma unroll
       for (int it = 0; it < 2; it++) load_item(src + ia.goff[it], p, v[it]);
     };
-    auto prefetch = [&](uint64_t tile) {
-      const uint64_t base = p.tile(tile);
+    auto prefetch = [&](uint64_t tbase) {
 #pragma unroll
       for (int it = 0; it < 2; it++) {
-        prefetch_item(state + base + ia.goff[it], p);
-        prefetch_item(adj + base + ia.goff[it], p);
+        prefetch_item(state + tbase + ia.goff[it], p);
+        prefetch_item(adj + tbase + ia.goff[it], p);
       }
     };
-    for (int k = 0; k < kPrefetch; k++)
-      if (blockIdx.x + (uint64_t)k * gridDim.x < p.ntiles) prefetch(blockIdx.x + (uint64_t)k * gridDim.x);
+    TileWalk wl, wp;   // base of the tile whose loads are issued next / of the tile prefetched into L2 next
+    wl.init(p, blockIdx.x, gridDim.x);
+    wp = wl;
+    // (L2 prefetch kRevPrefetch tiles ahead: off by default -- with the register pipeline a whole tile period ahead of
+    // its use the prefetch instructions only cost the fill ~1400 issue cycles per tile, profiles/r2_tc_rev_bench_v3.txt)
+    for (int k = 0; k < kRevPrefetch; k++) {
+      if (blockIdx.x + (uint64_t)k * gridDim.x < p.ntiles) prefetch(wp.cur);
+      wp.advance();
+    }
     uint32_t e_run_x = 0, e_run_y = 0;
     uint32_t it_count = 0;
     // Software pipeline over registers: the loads of the NEXT tile are issued as soon as the slices of this tile's
@@ -203,8 +212,8 @@ __global__ void __launch_bounds__(kRevThreads, 1)
     // bandwidth) is in flight while the fill computes, fences and waits for its stage.
     float4 vx[2][4], vy[2][4];
     if ((uint64_t)blockIdx.x < p.ntiles) {
-      load(state, blockIdx.x, vx);
-      load(adj, blockIdx.x, vy);
+      load(state, wl.cur, vx);
+      load(adj, wl.cur, vy);
     }
     for (uint64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, it_count++) {
       const int s = it_count & 1;
@@ -212,27 +221,33 @@ __global__ void __launch_bounds__(kRevThreads, 1)
       uint8_t* stage = smem + s * kRevStageBytes;
       const uint64_t next = tile + gridDim.x;
       if (t == 0) TC_TR(it_count, 0);
-      float mx = tile_max8(vx, sm_max + ((it_count & 1) * 2 + 0) * 8, warp, lane, 1);
-      e_run_x = max(e_run_x, (__float_as_uint(mx) >> 23) & 0xffu);
+      e_run_x = warp_grid_exp(vx, e_shared, e_run_x, lane);
       float m0, m1, m2;
       magic_of(e_run_x, m0, m1, m2);
       if (t == 0) TC_TR(it_count, 1);
-      if (use > 0) mbar_wait(&empty[s], (use - 1) & 1, p.error_flag);
+      if (use > 0) mbar_wait(&bar_b[s], (use - 1) & 1, p.error_flag);   // X slices of tile t - 2 are no longer read
       if (t == 0) TC_TR(it_count, 2);
       rev_fill_slices<false>(vx, ia.soff, m0, m1, m2, stage);
-      if (next < p.ntiles) load(state, next, vx);
+      wl.advance();
+      if (next < p.ntiles) load(state, wl.cur, vx);
       if (t == 0) TC_TR(it_count, 3);
-      mx = tile_max8(vy, sm_max + ((it_count & 1) * 2 + 1) * 8, warp, lane, 1);
-      if (t == 0) TC_TR(it_count, 4);
-      e_run_y = max(e_run_y, (__float_as_uint(mx) >> 23) & 0xffu);
+      e_run_y = warp_grid_exp(vy, e_shared + 1, e_run_y, lane);
       magic_of(e_run_y, m0, m1, m2);
+      if (use > 0) mbar_wait(&bar_c[s], (use - 1) & 1, p.error_flag);   // nor its conj(Y) slices
+      if (t == 0) TC_TR(it_count, 4);
       rev_fill_slices<true>(vy, ia.soff, m0, m1, m2, stage + kStageBytes);
-      if (next < p.ntiles) load(adj, next, vy);
-      if (tile + (uint64_t)kPrefetch * gridDim.x < p.ntiles) prefetch(tile + (uint64_t)kPrefetch * gridDim.x);
+      if (next < p.ntiles) load(adj, wl.cur, vy);
+      if (kRevPrefetch > 0) {
+        if (tile + (uint64_t)kRevPrefetch * gridDim.x < p.ntiles) prefetch(wp.cur);
+        wp.advance();
+      }
       if (t == 0) TC_TR(it_count, 5);
-      fence_async_smem();
-      if (t == 0) TC_TR(it_count, 6);
+      // (no fence.proxy.async here: it waits for the loads of the next tile that this thread has in flight -- up to
+      // 1800 cycles, profiles/r2_tc_rev_bench_v4.txt.  The MMA warp executes the proxy fence after it has acquired
+      // `full`: arrive (release) -> wait (acquire) -> fence.proxy.async -> tcgen05.mma keeps these stores in the
+      // causality order of the asynchronous reads.)
       mbar_arrive(&full[s]);
+      if (t == 0) TC_TR(it_count, 6);
     }
   } else if (warp == kFillWarps) {
     // =========================================================================== MMA issue
@@ -245,9 +260,8 @@ __global__ void __launch_bounds__(kRevThreads, 1)
     constexpr uint32_t idesc_h = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const uint32_t base = smem_u32(smem);
     const uint32_t acc0 = tmem_base + kRevTmA0, acc1 = tmem_base + kRevTmA1;
-    const uint32_t h0 = tmem_base + kRevTmH0, h1 = tmem_base + kRevTmH1;
-    const bool all8 = p.products >= 8;
-    const uint32_t w2_lo = desc_lo(smem_u32(sm_w2), 16);
+    const uint32_t hacc = tmem_base + kRevTmH;
+    const bool all8 = p.products >= 8, h6 = rp.h_products >= 6;
     // R(W^dagger) * (slices whose MN-major descriptor starts at b_lo): (0,0) alone into A0 (exact), the lower-order
     // products into A1
     auto block_products = [&](uint32_t b_lo) {
@@ -263,11 +277,7 @@ __global__ void __launch_bounds__(kRevThreads, 1)
           for (int ks = 0; ks < 8; ks++) {   // K = 16 per instruction = 8 TMEM columns of A, 16 rows of B
             const uint64_t bd = desc_at(b_lo, kDescHi, px * kSliceBytesX + ks * 2048);
             const uint32_t accumulate = lead ? (ks > 0) : !(first1 && ks == 0);
-            if (pw < 2) {
-              umma_bf16_ts(lead ? acc0 : acc1, tmem_base + (uint32_t)(pw * 64 + ks * 8), bd, idesc_blk, accumulate);
-            } else {
-              umma_bf16(acc1, desc_at(w2_lo, kDescHi, (ks >> 2) * 16384 + (ks & 3) * 32), bd, idesc_blk, accumulate);
-            }
+            umma_bf16_ts(lead ? acc0 : acc1, tmem_base + (uint32_t)(pw * 64 + ks * 8), bd, idesc_blk, accumulate);
           }
           if (!lead) first1 = false;
         }
@@ -285,6 +295,7 @@ __global__ void __launch_bounds__(kRevThreads, 1)
       const uint32_t use = it >> 1, win = it / kFlush;
       const bool first = (it % kFlush) == 0, last = (it % kFlush) == kFlush - 1 || it + 1 == (uint32_t)my_tiles;
       mbar_wait(&full[s], use & 1, p.error_flag);
+      fence_async_smem();   // generic-proxy stores of the fill warps (acquired through `full`) -> async-proxy reads of the MMAs
       if (first && win >= 1) mbar_wait(h_empty, (win - 1) & 1, p.error_flag);
       tc_fence_after();
       const uint32_t xs = base + s * kRevStageBytes, ys = xs + kStageBytes;
@@ -293,9 +304,9 @@ __global__ void __launch_bounds__(kRevThreads, 1)
       if (elect_one()) {
         TC_TR(it, 8);
         // H_a: orders 0 and 1
-        h_product(yk_lo, xk_lo, 0, 0, h0, first);
-        h_product(yk_lo, xk_lo, 0, 1, h1, first);
-        h_product(yk_lo, xk_lo, 1, 0, h1, false);
+        h_product(yk_lo, xk_lo, 0, 0, hacc, first);
+        h_product(yk_lo, xk_lo, 0, 1, hacc, false);
+        h_product(yk_lo, xk_lo, 1, 0, hacc, false);
         TC_TR(it, 9);
       }
       __syncwarp();
@@ -309,9 +320,11 @@ __global__ void __launch_bounds__(kRevThreads, 1)
         umma_commit(&bar_a[s]);
         TC_TR(it, 11);
         // H_b: order 2
-        h_product(yk_lo, xk_lo, 0, 2, h1, false);
-        h_product(yk_lo, xk_lo, 1, 1, h1, false);
-        h_product(yk_lo, xk_lo, 2, 0, h1, false);
+        if (h6) {
+          h_product(yk_lo, xk_lo, 0, 2, hacc, false);
+          h_product(yk_lo, xk_lo, 1, 1, hacc, false);
+          h_product(yk_lo, xk_lo, 2, 0, hacc, false);
+        }
         umma_commit(&bar_b[s]);
         if (last) umma_commit(h_done);
         TC_TR(it, 12);
@@ -354,13 +367,21 @@ __global__ void __launch_bounds__(kRevThreads, 1)
       for (int g = 0; g < 16; g++)   // n = 4 g .. 4 g + 3: half-buffer (g & 1), chunk g / 2
         *(float4*)(region + (g & 1) * kSliceBytesX + x_chunk_byte(mu, g >> 1)) = make_float4(d[4 * g], d[4 * g + 1], d[4 * g + 2], d[4 * g + 3]);
     };
-    auto write_out = [&](float2* dst, const uint8_t* region, float sign_im) {
+    // staging -> registers (the stage's region is free again once every drain thread has done this), registers -> HBM
+    auto read_staged = [&](const uint8_t* region, float4 (&r)[4][4]) {
 #pragma unroll
       for (int it = 0; it < 4; it++) {
-        const float4 r0 = *(const float4*)(region + ia.soff[it]);
-        const float4 r1 = *(const float4*)(region + kSliceBytesX + ia.soff[it]);
-        float4 i0 = *(const float4*)(region + ia.soff[it] + 8192u);
-        float4 i1 = *(const float4*)(region + kSliceBytesX + ia.soff[it] + 8192u);
+        r[it][0] = *(const float4*)(region + ia.soff[it]);
+        r[it][1] = *(const float4*)(region + kSliceBytesX + ia.soff[it]);
+        r[it][2] = *(const float4*)(region + ia.soff[it] + 8192u);
+        r[it][3] = *(const float4*)(region + kSliceBytesX + ia.soff[it] + 8192u);
+      }
+    };
+    auto write_out = [&](float2* dst, const float4 (&r)[4][4], float sign_im) {
+#pragma unroll
+      for (int it = 0; it < 4; it++) {
+        const float4 r0 = r[it][0], r1 = r[it][1];
+        float4 i0 = r[it][2], i1 = r[it][3];
         i0.x *= sign_im; i0.y *= sign_im; i0.z *= sign_im; i0.w *= sign_im;
         i1.x *= sign_im; i1.y *= sign_im; i1.z *= sign_im; i1.w *= sign_im;
         const float4 o[4] = {make_float4(r0.x, i0.x, r0.y, i0.y), make_float4(r0.z, i0.z, r0.w, i0.w),
@@ -368,14 +389,16 @@ __global__ void __launch_bounds__(kRevThreads, 1)
         store_item(dst + ia.goff[it], p, o);
       }
     };
+    TileWalk wd;
+    wd.init(p, blockIdx.x, gridDim.x);
     uint32_t it_count = 0;
-    for (uint64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, it_count++) {
+    for (uint64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, it_count++, wd.advance()) {
       const int s = it_count & 1;
       const uint32_t use = it_count >> 1, win = it_count / kFlush;
       const bool last = (it_count % kFlush) == kFlush - 1 || it_count + 1 == (uint32_t)my_tiles;
-      uint8_t* stage = smem + s * kRevStageBytes;
-      const uint64_t tbase = p.tile(tile);
+      const uint64_t tbase = wd.cur;
       float d[64];
+      float4 r[4][4];
       // ---- X'
       mbar_wait(&bar_a[s], use & 1, p.error_flag);
       tc_fence_after();
@@ -384,32 +407,28 @@ __global__ void __launch_bounds__(kRevThreads, 1)
       tc_fence_before();
       mbar_arrive(acc_empty);
       if (t128 == 0) TC_TR(it_count, 17);
-      mbar_wait(&bar_b[s], use & 1, p.error_flag);
-      tc_fence_after();
+      stage_out(sm_out, d);
+      named_bar(2, kDrainThreads);
+      read_staged(sm_out, r);
+      named_bar(2, kDrainThreads);                // every drain thread has read its staging rows
       if (t128 == 0) TC_TR(it_count, 18);
-      stage_out(stage, d);
       if (last) {
         // H window -> the CTA's private partial (single writer per element; red = no round trip)
         mbar_wait(h_done, win & 1, p.error_flag);
         tc_fence_after();
 #pragma unroll 1
-        for (int ch = 0; ch < 8; ch++) {
-          float a0[16], a1[16];
-          tmem_ld16(lane_addr + kRevTmH0 + ch * 16, a0);
-          tmem_ld16(lane_addr + kRevTmH1 + ch * 16, a1);
+        for (int ch = 0; ch < 4; ch++) {
+          float a0[32];
+          tmem_ld32(lane_addr + kRevTmH + ch * 32, a0);
           tmem_ld_wait();
 #pragma unroll
-          for (int g = 0; g < 4; g++)
-            red_add_v4(mine + ch * 16 + 4 * g, a0[4 * g] + a1[4 * g], a0[4 * g + 1] + a1[4 * g + 1], a0[4 * g + 2] + a1[4 * g + 2],
-                       a0[4 * g + 3] + a1[4 * g + 3]);
+          for (int g = 0; g < 8; g++) red_add_v4(mine + ch * 32 + 4 * g, a0[4 * g], a0[4 * g + 1], a0[4 * g + 2], a0[4 * g + 3]);
         }
         tc_fence_before();
         mbar_arrive(h_empty);
       }
       if (t128 == 0) TC_TR(it_count, 19);
-      named_bar(2, kDrainThreads);
-      if (t128 == 0) TC_TR(it_count, 20);
-      write_out(state + tbase, stage, 1.0f);
+      write_out(state + tbase, r, 1.0f);
       if (t128 == 0) TC_TR(it_count, 21);
       // ---- Y'
       mbar_wait(&bar_c[s], use & 1, p.error_flag);
@@ -419,14 +438,13 @@ __global__ void __launch_bounds__(kRevThreads, 1)
       tc_fence_before();
       mbar_arrive(acc_empty);
       if (t128 == 0) TC_TR(it_count, 23);
-      stage_out(stage + kStageBytes, d);
+      stage_out(sm_out, d);
       named_bar(2, kDrainThreads);
-      if (t128 == 0) TC_TR(it_count, 24);
-      write_out(adj + tbase, stage + kStageBytes, -1.0f);
+      read_staged(sm_out, r);
+      named_bar(2, kDrainThreads);
       if (t128 == 0) TC_TR(it_count, 25);
-      named_bar(2, kDrainThreads);                // every drain thread has read its staging rows
+      write_out(adj + tbase, r, -1.0f);
       if (t128 == 0) TC_TR(it_count, 26);
-      mbar_arrive(&empty[s]);
     }
   }
 

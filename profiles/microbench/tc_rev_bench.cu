@@ -3,7 +3,7 @@
 // throughput against the HBM roofline (4 * S of traffic).
 //
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -o tc_rev_bench tc_rev_bench.cu
-//   ./tc_rev_bench [n_check=22] [n_time=30] [first block qubit=8] [block list or -] [products=8]
+//   ./tc_rev_bench [n_check=22] [n_time=30] [first block qubit=8] [block list or -] [products=8] [h_products=6]
 #include <complex>
 #include <cstdio>
 #include <cstdlib>
@@ -58,6 +58,17 @@ static void apply_gate_to_rows(std::vector<zc>& w, const zc* g, int hi, int lo) 
   w.swap(out);
 }
 
+// timing runs: pseudo-random amplitudes generated on the device (the host generator needs ~30 s at 30 qubits)
+__global__ void k_fill_random(float2* x, size_t n, float scale, uint32_t seed) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    uint32_t h = (uint32_t)i * 2654435761u ^ (uint32_t)(i >> 32) * 40503u ^ seed;
+    h ^= h >> 15; h *= 2246822519u; h ^= h >> 13; h *= 3266489917u; h ^= h >> 16;
+    const float a = ((h & 0xffff) - 32768.0f) / 32768.0f, b = ((h >> 16) - 32768.0f) / 32768.0f;
+    x[i] = make_float2(a * scale, b * scale);
+  }
+}
+
+static int g_h_products = 6;
 static void run(int n, const int* block, int products, bool check) {
   tcb::RevParams rp;
   int wbit[6];
@@ -94,9 +105,10 @@ static void run(int n, const int* block, int products, bool check) {
   rp.geo.error_flag = d_err;
   rp.geo.w_image = d_img;
   rp.geo.products = products;
+  rp.h_products = g_h_products;
   const size_t N = (size_t)1 << n;
-  std::vector<float2> hx(N), hy(N);
-  {
+  std::vector<float2> hx(check ? N : 0), hy(check ? N : 0);
+  if (check) {
     std::normal_distribution<float> nd;
     const float sc = 1.0f / std::sqrt((float)N);
     for (size_t i = 0; i < N; i++) { hx[i] = make_float2(nd(rng) * sc, nd(rng) * sc); hy[i] = make_float2(nd(rng) * sc + sc, nd(rng) * sc); }
@@ -104,8 +116,15 @@ static void run(int n, const int* block, int products, bool check) {
   float2 *dx, *dy;
   CK(cudaMalloc(&dx, N * sizeof(float2)));
   CK(cudaMalloc(&dy, N * sizeof(float2)));
-  CK(cudaMemcpy(dx, hx.data(), N * sizeof(float2), cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(dy, hy.data(), N * sizeof(float2), cudaMemcpyHostToDevice));
+  if (check) {
+    CK(cudaMemcpy(dx, hx.data(), N * sizeof(float2), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dy, hy.data(), N * sizeof(float2), cudaMemcpyHostToDevice));
+  } else {
+    const float sc = 1.0f / std::sqrt((float)N);
+    k_fill_random<<<1184, 256>>>(dx, N, sc, 17u);
+    k_fill_random<<<1184, 256>>>(dy, N, sc, 99u);
+    CK(cudaDeviceSynchronize());
+  }
   int sms = 0;
   CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
   const int grid = (int)std::min<uint64_t>(rp.geo.ntiles, (uint64_t)sms);
@@ -172,6 +191,7 @@ static void run(int n, const int* block, int products, bool check) {
         eh = std::max(eh, std::abs(got - want));
         mh = std::max(mh, std::abs(want));
       }
+    printf("h_products=%d ", g_h_products);
     printf("n=%d block=%d,%d,%d,%d,%d,%d products=%d vs host double, max |err| / max |value|: state %.3e  adjoint %.3e  H %.3e (max entry %.3e)\n",
            n, block[0], block[1], block[2], block[3], block[4], block[5], products, ex / mxv, ey / myv, eh / mh, mh);
   } else {
@@ -187,7 +207,8 @@ static void run(int n, const int* block, int products, bool check) {
     float ms = 0;
     CK(cudaEventElapsedTime(&ms, e0, e1));
     ms /= reps;
-    const double mmas = (products >= 8 ? 128.0 : 96.0) * 2 * 128 * 64 * 16 + 24.0 * 2 * 128 * 128 * 16;
+    const double mmas = (products >= 8 ? 128.0 : 96.0) * 2 * 128 * 64 * 16 + (g_h_products >= 6 ? 24.0 : 12.0) * 2 * 128 * 128 * 16;
+    printf("h_products=%d ", g_h_products);
     printf("n=%d products=%d fused reverse step: %.3f ms = %.1f GB/s of HBM traffic (4 * S), %.1f TFLOP/s bf16 tensor\n", n, products, ms,
            4.0 * N * sizeof(float2) / ms * 1e-6, mmas * (double)rp.geo.ntiles / ms * 1e-9);
   }
@@ -228,6 +249,7 @@ int main(int argc, char** argv) {
     if (sscanf(argv[4], "%d,%d,%d,%d,%d,%d", block, block + 1, block + 2, block + 3, block + 4, block + 5) != 6) return 1;
   }
   const int products = argc > 5 ? atoi(argv[5]) : 8;
+  g_h_products = argc > 6 ? atoi(argv[6]) : 6;
   if (n_check > 0) run(n_check, block, products, true);
   if (n_time > 0) run(n_time, block, products, false);
   return 0;

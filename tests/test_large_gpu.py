@@ -79,8 +79,9 @@ def _reference(n, depth, precision):
     return out
 
 
-@pytest.mark.parametrize("precision", ["f32", "f64"])
-def test_default_tiles_match_the_unmodified_reference_at_30q(pkg, precision):
+@pytest.mark.parametrize("precision,options", [("f32", ()), ("f32", (("tc", 0),)), ("f64", ())],
+                         ids=["f32-default(tensor-core blocks)", "f32-fp32-tile-kernels", "f64"])
+def test_default_tiles_match_the_unmodified_reference_at_30q(pkg, precision, options):
     if not rr.ref_available(precision):
         pytest.skip("oracle/_ref not built (make -C oracle)")
     n, depth = 30, 4
@@ -88,11 +89,13 @@ def test_default_tiles_match_the_unmodified_reference_at_30q(pkg, precision):
     if _free_gib() < need:
         pytest.skip(f"needs {need} GiB of free device memory")
     tol = 1e-5 if precision == "f32" else 1e-12
-    (dens, grads), passes = _ours(n, depth, precision)            # library defaults: fuse = 2, 2^12 / 2^11 tiles
-    assert passes < 2 * 58 / 3, "the tiled executor must be the one that ran"
+    # library defaults: fuse = 2; f32: tensor-core 6-qubit blocks (tc = 0: 2^12 FP32 tiles); f64: 2^11 tiles
+    (dens, grads), passes = _ours(n, depth, precision, options)
+    assert passes < 2 * 58 / 3, "a fused executor must be the one that ran"
     dens_r, grads_r = _reference(n, depth, precision)
     ed, eg = _max_rel(dens, dens_r), _max_rel(grads, grads_r)
-    _record("30q_vs_reference", {"precision": precision, "depth": depth, "err_density": ed, "err_gradient": eg})
+    _record("30q_vs_reference", {"precision": precision, "options": dict(options), "depth": depth, "hbm_passes": passes,
+                                 "err_density": ed, "err_gradient": eg})
     assert ed < tol and eg < tol, (ed, eg)
 
 
@@ -130,3 +133,21 @@ def test_default_tiles_match_reference_and_per_gate_executor_at_32q(pkg):
         # |ours - ref| <= |ours - exact| + |ref - exact|: nothing beyond the reference's own rounding error
         assert rec["err_density_vs_reference"] < 1e-5 + rec["reference_err_density_vs_f64"], rec
         assert rec["err_gradient_vs_reference"] < 1e-5 + rec["reference_err_gradient_vs_f64"], rec
+
+
+def test_tensor_core_blocks_at_depth_40_against_the_f64_build_at_30q(pkg):
+    """Accumulated rounding of the tensor-core blocks at a realistic depth: 30 q brickwork depth 40 (620 gates, ~70
+    blocks forward, as many fused reverse steps) against the f64 build as arbiter (itself pinned to the reference's f64
+    build at 1e-15 above), with 8 (default) and 6 slice products per block, and the FP32 tile kernels beside them."""
+    n, depth = 30, 40
+    if _free_gib() < 2 * 16 + 2 * 8 + 4:
+        pytest.skip("needs 52 GiB of free device memory")
+    (dens64, grads64), _ = _ours(n, depth, "f64")
+    rec = {"precision": "f32", "depth": depth}
+    for name, options in (("tc8", (("tc", 1), ("tc_products", 8))), ("tc6", (("tc", 1), ("tc_products", 6))), ("fp32_tiles", (("tc", 0),))):
+        (dens, grads), _ = _ours(n, depth, "f32", options)
+        rec["err_density_" + name] = _max_rel(dens, dens64)
+        rec["err_gradient_" + name] = _max_rel(grads, grads64)
+    _record("30q_depth40_vs_f64", rec)
+    for name in ("tc8", "tc6", "fp32_tiles"):
+        assert rec["err_density_" + name] < 1e-5 and rec["err_gradient_" + name] < 1e-5, rec
