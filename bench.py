@@ -385,7 +385,7 @@ def load_peaks():
     return peak, src, float(peaks.get("sm_max_mhz", 1965.0))
 
 
-def roofline_block(prof, dev_ms, steps, precision, local_qubits, kinds, clocks, tc_rev=True):
+def roofline_block(prof, dev_ms, steps, precision, local_qubits, kinds, clocks, tc_rev=True, tc_products=6):
     """Dominant kernel = the category with the most device time.  `achieved` / `frac` follow SURVEY 8(d):
     algorithmic bytes (2*S forward, 4*S reverse PER GATE) over the launch time against the measured HBM copy
     peak -- above 1 when a launch applies several gates.  The binding resource of the tiled passes is the
@@ -432,7 +432,8 @@ def roofline_block(prof, dev_ms, steps, precision, local_qubits, kinds, clocks, 
         alg = 4 if name == "tc_bwd" else 2
         tiles = float(1 << (local_qubits - 12))
         mma_flop = 2.0 * 128 * 64 * 16                     # one tcgen05.mma of the block kernel (M 128, N 64, K 16)
-        per_tile = (2 * 64 + 24 * 2) * mma_flop if name == "tc_bwd" else 64 * mma_flop
+        blk = 8 * tc_products                              # MMAs of one block product (6 or 8 slice products x K / 16)
+        per_tile = (2 * blk + 24 * 2) * mma_flop if name == "tc_bwd" else blk * mma_flop
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -448,8 +449,9 @@ def roofline_block(prof, dev_ms, steps, precision, local_qubits, kinds, clocks, 
         r["tensor_tflops"] = round(per_tile * tiles * e["launches"] / sec / 1e12, 1)
         r["tensor_peak_tflops"] = tpeak
         r["tensor_frac"] = round(r["tensor_tflops"] / tpeak, 4)
-        r["tensor_note"] = ("bf16 tcgen05.mma on exact 9 / 8-bit slices of the f32 data, 64 (48 + 16) + 24 x 2 instructions "
-                            "of 128 x 64 x 16 per 2^12-amplitude tile; peak = measured cuBLAS bf16 (sustained)")
+        r["tensor_note"] = ("bf16 tcgen05.mma on exact 9-bit slices of the f32 data: %d instructions of 128 x 64 x 16 per block "
+                            "product and 2^12-amplitude tile%s; peak = measured cuBLAS bf16 (sustained)"
+                            % (blk, " (two block products + 24 of 128 x 128 x 16 for the block gradient)" if name == "tc_bwd" else ""))
         r["gates_per_launch"] = round(r["algorithmic_bytes_per_launch"] / float(alg * S), 2)
     return r
 
@@ -512,7 +514,8 @@ def run_workload(args, world, rank, local, precision, workload, local_qubits, de
                                   if "tc_fwd" in prof or "tc_bwd" in prof else "")},
         "effective_hbm_gbs": round(total_alg * world / (dev_ms * 1e-3) / 1e9, 1),
         "effective_hbm_frac": round(total_alg / (dev_ms * 1e-3) / 1e9 / peak, 4),
-        "roofline": roofline_block(prof, dev_ms, steps, precision, local_qubits, kinds, clocks, tc_rev=args.tc_rev != 0),
+        "roofline": roofline_block(prof, dev_ms, steps, precision, local_qubits, kinds, clocks, tc_rev=args.tc_rev != 0,
+                                   tc_products=args.tc_products or 6),
         "profile_ms": {k: round(v["ms"], 2) for k, v in sorted(prof.items())},
         "e2e": {"value": round(world * n_gates * steps / wall, 3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h)},

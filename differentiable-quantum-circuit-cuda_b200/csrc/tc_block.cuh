@@ -67,8 +67,10 @@ constexpr int kTmemAcc = 256;
 #ifndef TC_PREFETCH
 #define TC_PREFETCH 0
 #endif
-// tiles of L2 prefetch distance per CTA: 0 = off (default; with the fill's register pipeline a whole tile period ahead of
-// its use, the prefetch instructions only cost issue cycles -- profiles/r2_tc_rev_bench_v3.txt)
+// tiles of L2 prefetch distance per CTA (one cp.async.bulk.prefetch.L2 per 256-byte run).  0 = off, the default: the
+// fill's register pipeline already has a tile in flight half a period ahead of its use; prefetching on top of it made
+// the loads return at once but the kernels slower (30 q reverse step 10.17 / 10.54 / 11.11 ms at distance 0 / 4 / 8,
+// forward block 0.954 / 1.068 ms at 28 q: profiles/r2_tc_rev_bench_v7.txt)
 constexpr int kPrefetch = TC_PREFETCH;
 
 // Software bit deposit: tile number -> amplitude base (same role as TileGeo::tile)
@@ -244,6 +246,38 @@ __device__ __forceinline__ void slice3(float x, float m0, float m1, float m2, fl
   const float r2 = __fsub_rn(r1, p1);
   p2 = __fsub_rn(__fadd_rn(r2, m2), m2);
 }
+// the same for two values at once on the packed FP32 pipe (add / fma .f32x2 of sm_100: 8 instructions per PAIR)
+#ifndef TC_FADD2
+#define TC_FADD2 1
+#endif
+__device__ __forceinline__ void slice3_pair(float xa, float xb, float m0, float m1, float m2, float& a0, float& a1, float& a2,
+                                            float& b0, float& b1, float& b2) {
+#if TC_FADD2
+  unsigned long long x, M0, N0, M1, N1, M2, N2, neg1, t, q0, q1, q2, r1, r2;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(xa), "f"(xb));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(M0) : "f"(m0));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(N0) : "f"(-m0));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(M1) : "f"(m1));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(N1) : "f"(-m1));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(M2) : "f"(m2));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(N2) : "f"(-m2));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(neg1) : "f"(-1.0f));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(t) : "l"(x), "l"(M0));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(q0) : "l"(t), "l"(N0));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r1) : "l"(q0), "l"(neg1), "l"(x));     // x - p0 (exact)
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(t) : "l"(r1), "l"(M1));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(q1) : "l"(t), "l"(N1));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r2) : "l"(q1), "l"(neg1), "l"(r1));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(t) : "l"(r2), "l"(M2));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(q2) : "l"(t), "l"(N2));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(b0) : "l"(q0));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a1), "=f"(b1) : "l"(q1));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a2), "=f"(b2) : "l"(q2));
+#else
+  slice3(xa, m0, m1, m2, a0, a1, a2);
+  slice3(xb, m0, m1, m2, b0, b1, b2);
+#endif
+}
 // the high halves of two f32 words -> one word of two bf16 (lo = first)
 __device__ __forceinline__ uint32_t pack_hi16(float a, float b) {
   return __byte_perm(__float_as_uint(a), __float_as_uint(b), 0x7632);
@@ -294,6 +328,19 @@ __device__ __forceinline__ void prefetch_item(const float2* src, const Params& p
     asm volatile("prefetch.global.L2 [%0];" ::"l"(src + p.elem_off[2 * h]));
     if (!p.fast) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + p.elem_off[2 * h + 1]));
   }
+}
+// One instruction per 256-byte run: every tile holds the 5 lowest positions, so it is 128 contiguous runs of 32
+// amplitudes.  (The per-item prefetches above cost a fill thread 8 instructions per 64 bytes.)
+__device__ __forceinline__ void prefetch_run_l2(const float2* run_start) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], 256;" ::"l"(run_start) : "memory");
+}
+// amplitude offset of run r (0..127) of a tile: the bits of r on the tile's 7 upper positions
+__device__ __forceinline__ uint64_t run_offset(const Params& p, int r) {
+  uint64_t g = 0;
+#pragma unroll
+  for (int b = 0; b < 7; b++)
+    if ((r >> b) & 1) g |= 1ull << p.pos[5 + b];
+  return g;
 }
 __device__ __forceinline__ void store_item(float2* __restrict__ dst, const Params& p, const float4 (&v)[4]) {
   if (p.fast) {
@@ -413,14 +460,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_block_fwd(float2* __restrict
     TileWalk wl, wp;   // base of the tile whose loads are issued next / of the tile prefetched into L2 next
     wl.init(p, blockIdx.x, gridDim.x);
     wp = wl;
-    // L2 prefetch of the first tiles of this CTA
+    // L2 prefetch of the first tiles of this CTA: threads 0..127 own one 256-byte run each
+    const uint64_t roff = run_offset(p, t & 127);
     for (int k = 0; k < kPrefetch; k++) {
       const uint64_t tl = blockIdx.x + (uint64_t)k * gridDim.x;
-      if (tl < p.ntiles) {
-        const float2* src = state + wp.cur;
-#pragma unroll
-        for (int it = 0; it < 2; it++) prefetch_item(src + ia.goff[it], p);
-      }
+      if (tl < p.ntiles && t < 128) prefetch_run_l2(state + wp.cur + roff);
       wp.advance();
     }
     uint32_t it_count = 0, e_run = 0;
@@ -436,12 +480,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_block_fwd(float2* __restrict
     for (uint64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, it_count++) {
       const int s = it_count % kStages;
       const uint32_t use = it_count / kStages;
-      if (tile + (uint64_t)kPrefetch * gridDim.x < p.ntiles) {
-        const float2* src = state + wp.cur;
-#pragma unroll
-        for (int it = 0; it < 2; it++) prefetch_item(src + ia.goff[it], p);
+      if (kPrefetch > 0) {
+        if (tile + (uint64_t)kPrefetch * gridDim.x < p.ntiles && t < 128) prefetch_run_l2(state + wp.cur + roff);
+        wp.advance();
       }
-      wp.advance();
       // 9-bit slices: grids 2^(E - 8), 2^(E - 17), 2^(E - 26) with 2^E > max: |k_i| <= 256 is still exact in bf16
       // (8 significant bits) and the leading products stay exact: 128 * 2^16 = 2^23 < 2^24
       e_run = warp_grid_exp(v, e_shared, e_run, lane);
@@ -461,7 +503,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_block_fwd(float2* __restrict
         for (int c = 0; c < 2; c++) {
           float q0[8], q1[8], q2[8];
 #pragma unroll
-          for (int e = 0; e < 8; e++) slice3(c ? im[e] : re[e], m0, m1, m2, q0[e], q1[e], q2[e]);
+          for (int e = 0; e < 8; e += 2)
+            slice3_pair(c ? im[e] : re[e], c ? im[e + 1] : re[e + 1], m0, m1, m2, q0[e], q1[e], q2[e], q0[e + 1], q1[e + 1], q2[e + 1]);
           const uint32_t off = ia.soff[it] + (uint32_t)c * 8192u;   // row (c, j) = row j + 64
           *(uint4*)(stage + 0 * kSliceBytesX + off) =
               make_uint4(pack_hi16(q0[0], q0[1]), pack_hi16(q0[2], q0[3]), pack_hi16(q0[4], q0[5]), pack_hi16(q0[6], q0[7]));

@@ -26,7 +26,8 @@
 // (tcgen05.commit arrives on the barriers the fill waits on): the stage cycle is fill + MMA, not fill + MMA + drain.
 //
 // Warp roles (416 threads, one CTA per SM, persistent over tiles):
-//   warps 0-7  fill  : HBM (L2-prefetched) -> registers -> running tile maxima -> slices of X and conj(Y) -> `full`
+//   warps 0-7  fill  : HBM -> registers (the next tile's loads in flight) -> running maximum exponent per warp ->
+//                      slices of X and conj(Y) -> `full`
 //   warp  8    MMA   : one elected lane; per tile  H_a | X' -> A | H_b -> B | Y' -> C   (H split in two so that the
 //                      drain's tcgen05.ld of the single block accumulator pair always has tensor work to hide behind)
 //   warps 9-12 drain : A: X' accumulators -> registers (`acc_empty`) -> staging -> registers -> state;
@@ -100,8 +101,7 @@ __device__ __forceinline__ void rev_fill_slices(const float4 (&v)[2][4], const u
       for (int h = 0; h < 4; h++) {
         const float e0 = c ? (NEG_IM ? -v[it][h].y : v[it][h].y) : v[it][h].x;
         const float e1 = c ? (NEG_IM ? -v[it][h].w : v[it][h].w) : v[it][h].z;
-        slice3(e0, m0, m1, m2, q0[2 * h], q1[2 * h], q2[2 * h]);
-        slice3(e1, m0, m1, m2, q0[2 * h + 1], q1[2 * h + 1], q2[2 * h + 1]);
+        slice3_pair(e0, e1, m0, m1, m2, q0[2 * h], q1[2 * h], q2[2 * h], q0[2 * h + 1], q1[2 * h + 1], q2[2 * h + 1]);
       }
       const uint32_t off = soff[it] + (uint32_t)c * 8192u;   // row (c, j) = row j + 64
       *(uint4*)(slices + 0 * kSliceBytesX + off) =
@@ -189,18 +189,14 @@ __global__ void __launch_bounds__(kRevThreads, 1)
 #pragma unroll
       for (int it = 0; it < 2; it++) load_item(src + ia.goff[it], p, v[it]);
     };
-    auto prefetch = [&](uint64_t tbase) {
-#pragma unroll
-      for (int it = 0; it < 2; it++) {
-        prefetch_item(state + tbase + ia.goff[it], p);
-        prefetch_item(adj + tbase + ia.goff[it], p);
-      }
-    };
+    // L2 prefetch: threads 0..127 own one 256-byte run of the state tile each, threads 128..255 of the adjoint tile
+    const uint64_t roff = run_offset(p, t & 127);
+    const float2* pf_base = (t < 128 ? state : adj) + roff;
+    auto prefetch = [&](uint64_t tbase) { prefetch_run_l2(pf_base + tbase); };
     TileWalk wl, wp;   // base of the tile whose loads are issued next / of the tile prefetched into L2 next
     wl.init(p, blockIdx.x, gridDim.x);
     wp = wl;
-    // (L2 prefetch kRevPrefetch tiles ahead: off by default -- with the register pipeline a whole tile period ahead of
-    // its use the prefetch instructions only cost the fill ~1400 issue cycles per tile, profiles/r2_tc_rev_bench_v3.txt)
+    // (optional L2 prefetch kRevPrefetch tiles ahead, one bulk instruction per thread and tile; off by default, see kPrefetch)
     for (int k = 0; k < kRevPrefetch; k++) {
       if (blockIdx.x + (uint64_t)k * gridDim.x < p.ntiles) prefetch(wp.cur);
       wp.advance();

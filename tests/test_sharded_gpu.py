@@ -19,7 +19,17 @@ def _ngpus():
         return 0
 
 
-def _worker(rank, world, port, case, n, precision, fuse, peer, q):
+def _worker(rank, world, port, case, n, precision, fuse, peer, q, tc=0):
+    """A failing rank reports through the queue: the parent must not sit out its timeout on a multi-GPU box."""
+    try:
+        _worker_body(rank, world, port, case, n, precision, fuse, peer, q, tc)
+    except BaseException as e:  # noqa: BLE001
+        import traceback
+        q.put((rank, "error", f"{type(e).__name__}: {e}\n{traceback.format_exc()}", 0.0))
+        raise
+
+
+def _worker_body(rank, world, port, case, n, precision, fuse, peer, q, tc=0):
     import importlib
     import torch
     import torch.distributed as dist
@@ -36,7 +46,11 @@ def _worker(rank, world, port, case, n, precision, fuse, peer, q):
     dens_ref, cts_conj, grads_ref = reference_results(o, const, var)
     c = sharded.ShardedCircuit(n, precision=precision)
     c.set_option("fuse", fuse)
-    c.set_option("tile_bits", 11)
+    if tc:
+        c.set_option("tc", 1)          # tensor-core 6-qubit blocks on every shard (default only for shards >= 2^26)
+        c.set_option("profile", 1)
+    else:
+        c.set_option("tile_bits", 11)
     c.set_option("peer", peer)
     if peer:
         assert c.peer_exchange, "CUDA IPC peer mapping failed on an NVLink box"
@@ -45,6 +59,8 @@ def _worker(rank, world, port, case, n, precision, fuse, peer, q):
     cg, vg = [g.astype(dtype) for g in const], [g.astype(dtype) for g in var]
     dens = c.forward(cg, vg)
     grads = c.backward([x.astype(dtype) for x in cts_conj], cg, vg)
+    if tc and case != "autodiff":   # (autodiff: the windows hold NonU gates and keep the FP32 tile kernels in the reverse pass)
+        assert c.last_profile().get("tc_bwd", {}).get("launches", 0) > 0, "the tensor-core blocks must be the ones that ran"
     err_d = max(np.abs(a - b).max() for a, b in zip(dens, dens_ref))
     scale = max(np.abs(x).max() for x in grads_ref)
     err_g = max(np.abs(a - b).max() for a, b in zip(grads, grads_ref)) / scale
@@ -75,10 +91,35 @@ def test_sharded_matches_oracle(case, precision, world, fuse, peer):
     procs = [ctx.Process(target=_worker, args=(r, world, port, case, n, precision, fuse, peer, q)) for r in range(world)]
     for p in procs:
         p.start()
-    results = [q.get(timeout=600) for _ in range(world)]
+    results = [q.get(timeout=300) for _ in range(world)]
+    assert not any(r[1] == "error" for r in results), [r[2] for r in results if r[1] == "error"]
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
     tol = 1e-5 if precision == "f32" else 1e-12   # north_star tolerances
     for rank, err_d, err_g, err_s in results:
         assert err_d < tol and err_g < tol and err_s < tol * 10, (rank, err_d, err_g, err_s)
+
+
+@pytest.mark.parametrize("case", ["brickwork", "autodiff", "vqse"])
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_sharded_tensor_core_blocks_match_oracle(case, world):
+    """The f32 default of the measured sizes (tensor-core blocks, fused reverse step) on sharded registers: 2^14-amplitude
+    shards (the smallest a block pass accepts) with half-shard exchanges between the blocks."""
+    import torch.multiprocessing as mp
+    if _ngpus() < world:
+        pytest.skip(f"needs >= {world} GPUs")
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    n = 14 + world.bit_length() - 1
+    procs = [ctx.Process(target=_worker, args=(r, world, port, case, n, "f32", 2, 1, q, 1)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=300) for _ in range(world)]
+    assert not any(r[1] == "error" for r in results), [r[2] for r in results if r[1] == "error"]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for rank, err_d, err_g, err_s in results:
+        assert err_d < 1e-5 and err_g < 1e-5 and err_s < 1e-4, (rank, err_d, err_g, err_s)
