@@ -187,6 +187,63 @@ __global__ void __launch_bounds__(QDC_BLOCK)
   }
 }
 
+// ---- several (global qubit <-> local position) swaps in ONE exchange --------
+// The scheduler's remaps come in runs (35 q on 8 ranks: g0 <-> l4, g1 <-> l5, g2 <-> l6 back to back).  k swaps carried
+// out one after the other move k halves of the shard; done at once,
+//   new[local bits = b, rank bits = c] = old[local bits = c, rank bits = b]       (b, c: k-bit values),
+// this rank keeps the 2^-k of its shard with b == c and trades one 2^-k with each of the 2^k - 1 ranks of its group:
+// (1 - 2^-k) of a shard instead of k / 2 (7/8 instead of 3/2 for k = 3), all partners at once through the NVSwitch.
+// Element (local bits = b, x) of this rank trades places with element (local bits = c, x) of the rank whose selected
+// bits are b; of the two owners of such a pair the one with the smaller selected value handles the lower half of the
+// x range, the other one the upper half.
+struct MultiSwapArgs {
+  int k;                  // swapped pairs (2 or 3)
+  int pos_sorted[3];      // vector-index bit positions of the local qubits, ascending (zero insertion)
+  int pos_pair[3];        // ... in pair order: bit i of a selected value <-> pos_pair[i]
+  int c;                  // selected value of this rank
+  int half_log2;          // log2 of the x range each side owns per partner
+  void* peer[8];          // [b]: the same buffer on the rank whose selected bits are b
+};
+
+template <typename V>
+__global__ void __launch_bounds__(QDC_BLOCK) k_peer_multiswap(V* __restrict__ mine, const MultiSwapArgs a) {
+  const uint64_t stride = (uint64_t)gridDim.x * QDC_BLOCK;
+  const uint64_t per = 1ull << a.half_log2, total = per * (uint64_t)((1 << a.k) - 1);
+  constexpr int U = 4;
+  int dep_c = 0;
+  for (int i = 0; i < a.k; i++) dep_c |= ((a.c >> i) & 1) << a.pos_pair[i];
+  for (uint64_t w0 = (uint64_t)blockIdx.x * QDC_BLOCK + threadIdx.x; w0 < total; w0 += stride * U) {
+    V va[U], vb[U];
+    uint64_t mi[U], pi[U];
+    V* pp[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const uint64_t w = w0 + (uint64_t)u * stride;
+      if (w < total) {
+        const int j = (int)(w >> a.half_log2);
+        const int b = j < a.c ? j : j + 1;                      // partner's selected value (never c)
+        uint64_t x = (w & (per - 1ull)) + (a.c < b ? 0ull : per);
+        for (int i = 0; i < a.k; i++) x = ins0(x, a.pos_sorted[i]);
+        uint64_t dep_b = 0;
+        for (int i = 0; i < a.k; i++) dep_b |= (uint64_t)((b >> i) & 1) << a.pos_pair[i];
+        mi[u] = x | dep_b;
+        pi[u] = x | (uint64_t)dep_c;
+        pp[u] = (V*)a.peer[b];
+        va[u] = mine[mi[u]];
+        vb[u] = pp[u][pi[u]];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const uint64_t w = w0 + (uint64_t)u * stride;
+      if (w < total) {
+        mine[mi[u]] = vb[u];
+        pp[u][pi[u]] = va[u];
+      }
+    }
+  }
+}
+
 class Circuit {
  public:
   explicit Circuit(int n) : n_(n), n_loc_(n) {}
@@ -209,7 +266,8 @@ class Circuit {
   bool peer_ok_ = false;
   std::string peer_fail_;     // why the CUDA IPC mapping failed (reported by exchange() unless peer = 0)
   int opt_peer_ = 1;          // 1: peer-memory swap kernel when available, 0: NCCL send/recv + pack/unpack
-  int* d_token_ = nullptr;    // 2 ints: tokens of the stream-ordered pairwise barriers
+  int* d_token_ = nullptr;    // 1 + kMaxWorld ints: tokens of the stream-ordered barriers (send slot, one receive slot per rank)
+  int opt_multi_swap_ = 1;    // runs of remap swaps as ONE exchange with all ranks of the group (k_peer_multiswap)
   Workspace ws_;
   double* d_res_ = nullptr;  // device results: 32 doubles per slot
   size_t d_res_slots_ = 0;
@@ -305,8 +363,8 @@ class Circuit {
     QDC_TRY(ensure_state());
     if (world > 1) {
       QDC_CUDA(cudaMalloc((void**)&bwd_, bytes()));  // mapped by the partners: allocate up front
-      QDC_CUDA(cudaMalloc((void**)&d_token_, 2 * sizeof(int)));
-      QDC_CUDA(cudaMemset(d_token_, 0, 2 * sizeof(int)));
+      QDC_CUDA(cudaMalloc((void**)&d_token_, (1 + kMaxWorld) * sizeof(int)));
+      QDC_CUDA(cudaMemset(d_token_, 0, (1 + kMaxWorld) * sizeof(int)));
       setup_peers();
     }
     return nullptr;
@@ -338,8 +396,8 @@ class Circuit {
     if (d_mine) cudaFree(d_mine);
     if (d_all) cudaFree(d_all);
     int mapped = ok ? 1 : 0;
-    for (int j = 0; ok && (1 << j) < world_; j++) {
-      const int p = rank_ ^ (1 << j);
+    for (int p = 0; ok && p < world_; p++) {   // every rank: merged exchanges trade with all ranks of a group
+      if (p == rank_) continue;
       void *ps = nullptr, *pb = nullptr;
       if (cudaIpcOpenMemHandle(&ps, all[p].s, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
           cudaIpcOpenMemHandle(&pb, all[p].b, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
@@ -788,6 +846,81 @@ class Circuit {
     return nullptr;
   }
 
+  // Stream-ordered rendezvous with several partners at once (one NCCL group).
+  const char* group_barrier(const int* partners, int count) {
+    qdc::NcclApi& api = qdc::nccl();
+    int rc = api.GroupStart();
+    for (int i = 0; i < count && rc == 0; i++) {
+      rc = api.Send(d_token_, sizeof(int), qdc::kNcclChar, partners[i], comm_, stream_);
+      if (rc == 0) rc = api.Recv(d_token_ + 1 + partners[i], sizeof(int), qdc::kNcclChar, partners[i], comm_, stream_);
+    }
+    const int rc2 = api.GroupEnd();
+    if (rc == 0) rc = rc2;
+    if (rc != 0) return qdc_errf("NCCL barrier failed: %s", api.GetErrorString(rc));
+    return nullptr;
+  }
+
+  // Can the swaps (gbit[i] <-> lpos[i]), i < k, run as one merged exchange?
+  bool multi_swap_ok(int k, const int* lpos) const {
+    if (!(peer_ok_ && opt_peer_ && opt_multi_swap_) || k < 2 || k > 3) return false;
+    for (int i = 0; i < k; i++)
+      if (lpos[i] < QDC_LV) return false;
+    return n_loc_ - QDC_LV - k - 1 >= 0;
+  }
+
+  // k simultaneous swaps gbit[i] <-> lpos[i] of buffer `buf` (k_peer_multiswap)
+  const char* exchange_multi(cplx_t* buf, int k, const int* gbit, const int* lpos) {
+    MultiSwapArgs a;
+    a.k = k;
+    a.c = 0;
+    for (int i = 0; i < k; i++) {
+      a.c |= ((rank_ >> gbit[i]) & 1) << i;
+      a.pos_pair[i] = lpos[i] - QDC_LV;
+      a.pos_sorted[i] = lpos[i] - QDC_LV;
+    }
+    std::sort(a.pos_sorted, a.pos_sorted + k);
+    a.half_log2 = n_loc_ - QDC_LV - k - 1;
+    int partners[8], np = 0;
+    for (int b = 0; b < (1 << k); b++) {
+      a.peer[b] = nullptr;
+      if (b == a.c) continue;
+      int p = rank_;
+      for (int i = 0; i < k; i++) p = (p & ~(1 << gbit[i])) | (((b >> i) & 1) << gbit[i]);
+      a.peer[b] = (buf == state_) ? (void*)peer_state_[p] : (void*)peer_bwd_[p];
+      if (!a.peer[b]) return qdc_errf("internal: rank %d is not mapped for the merged exchange.", p);
+      partners[np++] = p;
+    }
+    DeviceInfo di;
+    QDC_TRY(qdc_device_info(&di));
+    QDC_TRY(group_barrier(partners, np));   // every rank of the group is done with everything before the exchange
+    const uint64_t total = (uint64_t)((1 << k) - 1) << a.half_log2;
+    const int grid = pick_grid(total, 4, 8, di.sm_count);
+    k_peer_multiswap<vec_t><<<grid, QDC_BLOCK, 0, stream_>>>((vec_t*)buf, a);
+    QDC_CUDA(cudaGetLastError());
+    QDC_TRY(group_barrier(partners, np));   // the partners' halves of the pairs have landed here too
+    account(1, 1, 0);
+    return nullptr;
+  }
+
+  // The run of consecutive SWAP steps starting at plan step `si` (walking by `dir` = +1 / -1) that can be merged:
+  // returns how many (1 = no merge) and their (gbit, lpos).
+  int swap_run(size_t si, int dir, int* gbit, int* lpos) const {
+    const std::vector<qdc::Step>& steps = plan_.steps;
+    int k = 0;
+    for (size_t j = si; j < steps.size() && k < 3; j += (size_t)dir) {   // (j wraps past 0 to SIZE_MAX: loop ends)
+      const qdc::Step& t = steps[j];
+      if (t.type != qdc::ST_SWAP) break;
+      bool clash = false;
+      for (int i = 0; i < k; i++) clash |= gbit[i] == t.gbit || lpos[i] == t.lpos;
+      if (clash) break;
+      gbit[k] = t.gbit;
+      lpos[k] = t.lpos;
+      k++;
+    }
+    if (k >= 2 && !multi_swap_ok(k, lpos)) return 1;
+    return k;
+  }
+
   const char* exchange(cplx_t* buf, int gbit, int lpos) {
     if (peer_ok_ && opt_peer_) return exchange_peer(buf, gbit, lpos);
     // No silent performance cliff (the NCCL path runs at ~2/3 of the peer kernel's rate and needs 2 x half a
@@ -919,9 +1052,17 @@ class Circuit {
           if (opt_fuse_ >= 2) QDC_TRY(run_tile_forward_blocked(st, gp, false));
           else QDC_TRY(run_tile_forward(st, gp));
           break;
-        case qdc::ST_SWAP:
-          PROF(CAT_EXCHANGE, 0, exchange(state_, st.gbit, st.lpos));
+        case qdc::ST_SWAP: {
+          int gb[3], lp[3];
+          const int k = swap_run(si, +1, gb, lp);
+          if (k >= 2) {
+            PROF(CAT_EXCHANGE, 0, exchange_multi(state_, k, gb, lp));
+            si += (size_t)(k - 1);
+          } else {
+            PROF(CAT_EXCHANGE, 0, exchange(state_, st.gbit, st.lpos));
+          }
           break;
+        }
         case qdc::ST_DENS: {
           size_t sj = si;  // the run of densities requested at this program point
           while (sj + 1 < steps.size() && steps[sj + 1].type == qdc::ST_DENS) sj++;
@@ -1130,10 +1271,19 @@ class Circuit {
             QDC_TRY(run_tile_backward(st, gp, vslot, live));
           }
           break;
-        case qdc::ST_SWAP:
-          PROF(CAT_EXCHANGE, 0, exchange(state_, st.gbit, st.lpos));
-          if (live) PROF(CAT_EXCHANGE, 0, exchange(bwd_, st.gbit, st.lpos));
+        case qdc::ST_SWAP: {
+          int gb[3], lp[3];
+          const int k = swap_run(si, -1, gb, lp);
+          if (k >= 2) {
+            PROF(CAT_EXCHANGE, 0, exchange_multi(state_, k, gb, lp));
+            if (live) PROF(CAT_EXCHANGE, 0, exchange_multi(bwd_, k, gb, lp));
+            si -= (size_t)(k - 1);
+          } else {
+            PROF(CAT_EXCHANGE, 0, exchange(state_, st.gbit, st.lpos));
+            if (live) PROF(CAT_EXCHANGE, 0, exchange(bwd_, st.gbit, st.lpos));
+          }
           break;
+        }
       }
     }
     return nullptr;

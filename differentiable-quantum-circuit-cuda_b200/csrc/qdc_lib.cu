@@ -138,6 +138,7 @@ QDC_EXPORT const char* qdc_circuit_set_option(qdc_circuit* c, const char* key, l
   else if (strcmp(key, "batch_dens") == 0) c->impl.opt_batch_dens_ = (int)value;  // 0: one sweep per density / seed
   else if (strcmp(key, "soa") == 0) c->impl.opt_soa_ = (int)value;    // f32 tile kernels: 0 selects the interleaved-layout kernels
   else if (strcmp(key, "peer") == 0) c->impl.opt_peer_ = (int)value;  // 0: force the NCCL send/recv exchange
+  else if (strcmp(key, "multi_swap") == 0) c->impl.opt_multi_swap_ = (int)value;  // 0: one exchange per swapped qubit
   else if (strcmp(key, "tc") == 0) {   // f32: tensor-core fused 6-qubit blocks (tc_exec.cuh)
 #ifdef QDC_F64
     if (value > 0) return qdc_errf("option \"tc\" exists in the f32 build only.");

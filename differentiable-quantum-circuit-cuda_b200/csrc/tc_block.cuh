@@ -364,22 +364,28 @@ __device__ __forceinline__ void magic_of(uint32_t bexp, float& m0, float& m1, fl
   m2 = __uint_as_float(m0b - (18u << 23));
 }
 
-// Slicing grid of a fill warp WITHOUT a CTA-wide barrier: the exponent of the largest |value| this warp holds (one REDUX),
-// raised to the running maximum the warps of the CTA publish in shared memory (monotone, read without synchronisation).
-// The slices are ordinary f32 / bf16 VALUES, so a warp that is briefly one binade ahead of the others costs nothing but
-// the slack of the exactness bound (K = 128 leading products of <= 2^16 grid units leave one binade below 2^24), and the
-// absolute quantisation error stays 2^-27 of the largest amplitude this CTA has seen.
-__device__ __forceinline__ uint32_t warp_grid_exp(const float4 (&v)[2][4], uint32_t* e_shared, uint32_t e_run, int lane) {
+// Slicing grid of a fill warp WITHOUT a CTA-wide barrier per tile: the exponent of the largest |value| this warp holds
+// (one REDUX), raised to the warp's own running maximum.  The fill warps agree ONCE, on the first tile of the CTA
+// (fill_grid_seed: one named barrier per kernel), and from then on each warp only ever raises its own grid: the result is
+// deterministic (no unsynchronised reads), and the slices are ordinary f32 / bf16 VALUES, so a warp that is a binade
+// ahead of the others costs nothing but the slack of the exactness bound (K = 128 leading products of <= 2^16 grid
+// units leave one binade below 2^24).  The absolute quantisation error stays 2^-27 of the largest amplitude the warp has
+// seen.
+__device__ __forceinline__ uint32_t warp_max_exp(const float4 (&v)[2][4]) {
   float mx = 0.f;
 #pragma unroll
   for (int it = 0; it < 2; it++)
 #pragma unroll
     for (int h = 0; h < 4; h++)
       mx = fmaxf(fmaxf(mx, fmaxf(fabsf(v[it][h].x), fabsf(v[it][h].y))), fmaxf(fabsf(v[it][h].z), fabsf(v[it][h].w)));
-  const uint32_t e = __reduce_max_sync(0xffffffffu, (__float_as_uint(mx) >> 23) & 0xffu);
-  const uint32_t es = *(volatile uint32_t*)e_shared;
-  if (e > es && lane == 0) atomicMax(e_shared, e);
-  return max(e_run, max(e, es));
+  return __reduce_max_sync(0xffffffffu, (__float_as_uint(mx) >> 23) & 0xffu);
+}
+// common starting grid of the fill warps: the maximum exponent of the CTA's first tile (e_shared: zero on entry)
+__device__ __forceinline__ uint32_t fill_grid_seed(const float4 (&v)[2][4], uint32_t* e_shared, int lane) {
+  const uint32_t e = warp_max_exp(v);
+  if (lane == 0) atomicMax(e_shared, e);
+  named_bar(1, kFillThreads);
+  return *(volatile uint32_t*)e_shared;
 }
 
 // ------------------------------------------------------------------------------------ the kernel
@@ -405,7 +411,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_block_fwd(float2* __restrict
   uint64_t* mma_done = bars + 2 * kStages;     // [kStages]    MMA -> drain   (tcgen05.commit)
   uint64_t* tmem_empty = bars + 3 * kStages;   // [kAccStages] drain -> MMA   (128 arrivals)
   uint32_t* tmem_slot = (uint32_t*)(bars + 3 * kStages + kAccStages);
-  uint32_t* e_shared = tmem_slot + 2;          // running maximum exponent of the fill warps (warp_grid_exp)
+  uint32_t* e_shared = tmem_slot + 2;          // maximum exponent of the CTA's first tile (fill_grid_seed)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -476,6 +482,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_block_fwd(float2* __restrict
       const float2* src = state + wl.cur;
 #pragma unroll
       for (int it = 0; it < 2; it++) load_item(src + ia.goff[it], p, v[it]);
+      e_run = fill_grid_seed(v, e_shared, lane);
     }
     for (uint64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, it_count++) {
       const int s = it_count % kStages;
@@ -486,7 +493,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_block_fwd(float2* __restrict
       }
       // 9-bit slices: grids 2^(E - 8), 2^(E - 17), 2^(E - 26) with 2^E > max: |k_i| <= 256 is still exact in bf16
       // (8 significant bits) and the leading products stay exact: 128 * 2^16 = 2^23 < 2^24
-      e_run = warp_grid_exp(v, e_shared, e_run, lane);
+      e_run = max(e_run, warp_max_exp(v));
       float m0, m1, m2;
       magic_of(e_run, m0, m1, m2);
       if (use > 0) mbar_wait(&empty[s], (use - 1) & 1, p.error_flag);

@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(kRevThreads, 1)
   uint64_t* h_done = bars + 11;      // MMA -> drain: the H window is complete
   uint64_t* h_empty = bars + 12;     // drain -> MMA: H accumulators have been flushed
   uint32_t* tmem_slot = (uint32_t*)(bars + 13);
-  uint32_t* e_shared = tmem_slot + 2;        // [2] running maximum exponents of state / adjoint (warp_grid_exp)
+  uint32_t* e_shared = tmem_slot + 2;        // [2] maximum exponents of the CTA's first state / adjoint tile (fill_grid_seed)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -210,6 +210,8 @@ __global__ void __launch_bounds__(kRevThreads, 1)
     if ((uint64_t)blockIdx.x < p.ntiles) {
       load(state, wl.cur, vx);
       load(adj, wl.cur, vy);
+      e_run_x = fill_grid_seed(vx, e_shared, lane);
+      e_run_y = fill_grid_seed(vy, e_shared + 1, lane);
     }
     for (uint64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, it_count++) {
       const int s = it_count & 1;
@@ -217,7 +219,7 @@ __global__ void __launch_bounds__(kRevThreads, 1)
       uint8_t* stage = smem + s * kRevStageBytes;
       const uint64_t next = tile + gridDim.x;
       if (t == 0) TC_TR(it_count, 0);
-      e_run_x = warp_grid_exp(vx, e_shared, e_run_x, lane);
+      e_run_x = max(e_run_x, warp_max_exp(vx));
       float m0, m1, m2;
       magic_of(e_run_x, m0, m1, m2);
       if (t == 0) TC_TR(it_count, 1);
@@ -227,7 +229,7 @@ __global__ void __launch_bounds__(kRevThreads, 1)
       wl.advance();
       if (next < p.ntiles) load(state, wl.cur, vx);
       if (t == 0) TC_TR(it_count, 3);
-      e_run_y = warp_grid_exp(vy, e_shared + 1, e_run_y, lane);
+      e_run_y = max(e_run_y, warp_max_exp(vy));
       magic_of(e_run_y, m0, m1, m2);
       if (use > 0) mbar_wait(&bar_c[s], (use - 1) & 1, p.error_flag);   // nor its conj(Y) slices
       if (t == 0) TC_TR(it_count, 4);

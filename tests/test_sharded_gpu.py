@@ -61,6 +61,25 @@ def _worker_body(rank, world, port, case, n, precision, fuse, peer, q, tc=0):
     grads = c.backward([x.astype(dtype) for x in cts_conj], cg, vg)
     if tc and case != "autodiff":   # (autodiff: the windows hold NonU gates and keep the FP32 tile kernels in the reverse pass)
         assert c.last_profile().get("tc_bwd", {}).get("launches", 0) > 0, "the tensor-core blocks must be the ones that ran"
+    if tc and world >= 4:
+        # merged multi-qubit exchanges (k_peer_multiswap) against one exchange per swapped qubit: pure data movement,
+        # so the results agree to the last bits, with fewer exchange launches
+        ex1 = c.last_profile().get("exchange", {}).get("launches", 0)
+        c0 = sharded.ShardedCircuit(n, precision=precision)
+        for k, v in (("fuse", fuse), ("tc", 1), ("profile", 1), ("peer", peer), ("multi_swap", 0)):
+            c0.set_option(k, v)
+        for inst in o.instructions:
+            c0._add(*inst)
+        dens0 = c0.forward(cg, vg)
+        grads0 = c0.backward([x.astype(dtype) for x in cts_conj], cg, vg)
+        ex0 = c0.last_profile().get("exchange", {}).get("launches", 0)
+        sc = max(np.abs(x).max() for x in grads0)
+        assert max(np.abs(a - b).max() for a, b in zip(dens, dens0)) < 1e-6, "merged exchange changed the densities"
+        assert max(np.abs(a - b).max() for a, b in zip(grads, grads0)) / sc < 1e-6, "merged exchange changed the gradients"
+        assert ex1 <= ex0, (ex1, ex0)
+        if case == "brickwork":
+            assert ex1 < ex0, ("no run of swaps was merged", ex1, ex0)
+        del c0
     err_d = max(np.abs(a - b).max() for a, b in zip(dens, dens_ref))
     scale = max(np.abs(x).max() for x in grads_ref)
     err_g = max(np.abs(a - b).max() for a, b in zip(grads, grads_ref)) / scale
