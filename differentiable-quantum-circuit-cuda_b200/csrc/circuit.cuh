@@ -220,8 +220,11 @@ __global__ void __launch_bounds__(QDC_BLOCK) k_peer_multiswap(V* __restrict__ mi
     for (int u = 0; u < U; u++) {
       const uint64_t w = w0 + (uint64_t)u * stride;
       if (w < total) {
+        // partner of phase j: c XOR (j + 1) -- a perfect matching of the group in every phase, so each rank trades with
+        // exactly one partner at a time, both ways.  (Enumerating "every value but c" in ascending order sent two ranks
+        // to the same partner at once: 371 instead of 695 GB/s per direction, profiles/r2_bench_8gpu_35q_multiswap_v1.json.)
         const int j = (int)(w >> a.half_log2);
-        const int b = j < a.c ? j : j + 1;                      // partner's selected value (never c)
+        const int b = a.c ^ (j + 1);
         uint64_t x = (w & (per - 1ull)) + (a.c < b ? 0ull : per);
         for (int i = 0; i < a.k; i++) x = ins0(x, a.pos_sorted[i]);
         uint64_t dep_b = 0;

@@ -49,7 +49,7 @@ def multiswap_as_the_kernel_does_it(shards, gbits, lposs, lv):
             peer[b] = p
         for w in range(per * ((1 << k) - 1)):
             j = w >> half_log2
-            b = j if j < c else j + 1
+            b = c ^ (j + 1)
             x = (w & (per - 1)) + (0 if c < b else per)
             for i in range(k):
                 x = ins0(x, pos_sorted[i])
