@@ -453,6 +453,10 @@ def roofline_block(prof, dev_ms, steps, precision, local_qubits, kinds, clocks, 
                             "product and 2^12-amplitude tile%s; peak = measured cuBLAS bf16 (sustained)"
                             % (blk, " (two block products + 24 of 128 x 128 x 16 for the block gradient)" if name == "tc_bwd" else ""))
         r["gates_per_launch"] = round(r["algorithmic_bytes_per_launch"] / float(alg * S), 2)
+        r["binding_resource"] = ("neither roof alone: real DRAM traffic runs at dram_frac of the measured copy peak and the tcgen05 MMAs at "
+                                 "tensor_frac of the measured cuBLAS bf16 rate; ncu (profiles/r2_tc_rev_28q_v7_ncu.txt) shows the L1 data pipe, "
+                                 "shared by the tensor-core operand reads and the fill / drain traffic, at 64 % and the board under its "
+                                 "power cap (see clocks); frac > 1 is the ~9 gates fused per sweep")
     return r
 
 
