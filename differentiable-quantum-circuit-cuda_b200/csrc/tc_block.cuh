@@ -9,33 +9,39 @@
 //
 // Precision.  TF32 / BF16 products alone carry 2^-11 / 2^-8 relative error, and tensor-core FP32
 // accumulation truncates (round-toward-zero), which at ~50 accumulations per output is a SYSTEMATIC
-// shrink of ~5e-7 per block -- 1e-5 after the ~35 blocks a depth-100 amplitude passes through.  The
-// kernel therefore works on exact slices: every f32 value x of a tile is split, on the tile-uniform
-// grid g0 = 2^(E-7) (2^E > max |x| of the tile), into three BF16 numbers
+// shrink of ~5e-7 per block -- more than 1e-5 after the ~70 block applications (forward + un-compute) a depth-100
+// amplitude passes through.  The kernels therefore work on exact slices: every f32 value x of a tile is split, on the
+// grid g0 = 2^(E-8) (2^E > the largest |x| the fill warp has seen, see warp_max_exp / fill_grid_seed), into three
+// BF16 numbers of 9 significant bits each
 //
-//     x = p0 + p1 + p2 + r,   p_i = k_i * g0 * 2^(-8 i),  |k_i| <= 128,  |r| <= 2^(E-24)
-//     (forward kernel: 9 bits per slice, g0 = 2^(E-8), p_i = k_i * g0 * 2^(-9 i), |k_i| <= 256, |r| <= 2^(E-27))
+//     x = p0 + p1 + p2 + r,   p_i = k_i * g0 * 2^(-9 i),  |k_i| <= 256,  |r| <= 2^(E-27)
 //
-// (three magic-number roundings, 8 FADD per value; the high 16 bits of each f32 slice ARE the bf16).
-// W is sliced the same way on the host (grid 2^-7).  The leading products p0(W) * p0(X) are integers
-// times g0 * 2^-7 of at most 2^14; their sum over K = 128 stays below 2^24, so the tensor core adds
-// them EXACTLY in its own TMEM accumulator A0 whatever its rounding mode.  The seven lower-order
-// products (all but p2 * p2) go to a second accumulator A1 whose truncation errors are 2^-8 smaller
-// than the result's last bit.  D = A0 + A1 is one rounded f32 addition in the epilogue.  Error per
-// block: the 2^-24 * (tile max) quantisation of the inputs, unbiased.
+// (three magic-number roundings on the packed FP32 pipe, 8 add / fma.rn.f32x2 per PAIR of values; the high 16 bits
+// of each f32 slice ARE the bf16: |k| <= 256 is exact in its 8 significant bits).  W is sliced the same way on the
+// host (grid 2^-8 for unitaries).  The leading products p0(W) * p0(X) are integers of at most 2^16 on a common grid;
+// their sum over K = 128 stays below 2^24, so the tensor core adds them EXACTLY in its own TMEM accumulator A0 whatever
+// its rounding mode.  The lower-order products -- orders 1 and 2 by default (6 products in all), order 3 as well with
+// `products` = 8 -- go to a second accumulator A1 whose truncation errors are 2^-9 smaller than the result's last bit.
+// D = A0 + A1 is one rounded f32 addition in the epilogue.  Error per block: the quantisation of the inputs, unbiased
+// (measured against a double-precision host evaluation: 6e-8 (8 products) / 2.7e-7 (6) of the largest amplitude).
 //
-// Shared-memory layouts (what the UMMA descriptors describe):
-//   * W slice i : A operand, K-major, SWIZZLE_128B, bf16: two K blocks of 64 (128 B rows), 128 rows.
-//   * X slice j : B operand, MN-major (n contiguous), SWIZZLE_128B, bf16: row kappa = 128 B = 64 n.
+// Operand layouts (what the UMMA descriptors describe):
+//   * W slice i : A operand in TENSOR MEMORY (lane = row mu, 32-bit column = two bf16 along K: 64 columns per slice),
+//     copied once per launch from the global image of make_w_image with tcgen05.st.
+//   * X slice j : B operand in shared memory, MN-major (n contiguous), SWIZZLE_128B, bf16: row kappa = 128 B = 64 n.
+//     The block-gradient products of tc_rev.cuh read the SAME slices along their rows (K-major descriptors).
 //   * output staging (f32), two half-buffers with the SAME row / chunk structure as an X slice, so that the
 //     drain is the mirror image of the fill.
 // The fill goes through registers (LDG.128 -> slices -> STS.128): the slicing needs the CUDA cores
 // anyway, and the interleaved (re, im) HBM layout of the reference is de-interleaved on the way.
 //
-// Warp roles (288 threads, one CTA per SM, persistent over tiles, 2-stage pipeline):
-//   warps 0-3  fill    : HBM -> registers -> tile max -> slices -> smem stage, arrive `full`
-//   warp  4    MMA     : one elected lane issues 64 tcgen05.mma per tile, tcgen05.commit -> `mma_done`
-//   warps 5-8  drain   : tcgen05.ld A0, A1 -> D -> smem staging -> HBM, arrive `tmem_empty`, `empty`
+// Kernels: k_tc_block_fwd (state <- W state: forward blocks, and W^dagger / W^T for the three-sweep reverse step),
+// k_tc_block_grad (stand-alone block gradient of the three-sweep reverse step, option tc_rev = 0) and, in tc_rev.cuh,
+// k_tc_block_rev (the fused reverse step that the executor uses by default).  Warp roles of all three (416 threads,
+// one CTA per SM, persistent over tiles):
+//   warps 0-7  fill  : HBM -> registers (the next tile's loads in flight) -> slicing grid -> slices -> smem stage, arrive `full`
+//   warp  8    MMA   : converged warp, ONE elect.sync lane issues the tcgen05.mma of a tile, tcgen05.commit -> mbarrier
+//   warps 9-12 drain : tcgen05.ld A0, A1 -> D -> smem staging -> registers -> HBM
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -393,12 +399,12 @@ __device__ __forceinline__ uint32_t fill_grid_seed(const float4 (&v)[2][4], uint
 // qubits is multiplied by W.
 //
 // Warp roles (416 threads, one CTA per SM, persistent over tiles):
-//   warps 0-7   fill  : HBM -> registers (next tile prefetched while this one is sliced) -> tile max -> slices ->
-//                       smem stage (4 stages), arrive `full`
-//   warp  8     MMA   : one lane issues 48 / 64 tcgen05.mma per tile (A = W slices in TMEM, B = X slices in smem),
-//                       tcgen05.commit -> `mma_done`
+//   warps 0-7   fill  : HBM -> registers (the next tile's loads are issued as soon as this tile has been sliced) ->
+//                       slicing grid (per warp, seeded once per kernel) -> slices -> smem stage (4 stages), arrive `full`
+//   warp  8     MMA   : converged warp, proxy fence after `full`, one elected lane issues 48 / 64 tcgen05.mma per tile
+//                       (A = W slices in TMEM, B = X slices in smem), tcgen05.commit -> `mma_done`
 //   warps 9-12  drain : tcgen05.ld A0, A1 -> D = A0 + A1 -> smem staging (the stage's own, now dead, X slices) ->
-//                       HBM; arrive `tmem_empty` (2 accumulator stages) and `empty`
+//                       registers, arrive `tmem_empty` (2 accumulator stages) and `empty` -> HBM
 __global__ void __launch_bounds__(kThreads, 1) k_tc_block_fwd(float2* __restrict__ state, const __grid_constant__ Params p) {
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B atoms: 1024-byte aligned (pointer arithmetic on the array keeps the shared state space: a cast
