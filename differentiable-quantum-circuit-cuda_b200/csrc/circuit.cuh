@@ -271,6 +271,8 @@ class Circuit {
   int opt_peer_ = 1;          // 1: peer-memory swap kernel when available, 0: NCCL send/recv + pack/unpack
   int* d_token_ = nullptr;    // 1 + kMaxWorld ints: tokens of the stream-ordered barriers (send slot, one receive slot per rank)
   int opt_multi_swap_ = 1;    // runs of remap swaps as ONE exchange with all ranks of the group (k_peer_multiswap)
+  int opt_auto_swap_pos_ = 1; // sharded: lowest position of the remap victims chosen by the cost model (scheduler.hpp)
+  int chosen_swap_min_pos_ = -1;
   Workspace ws_;
   double* d_res_ = nullptr;  // device results: 32 doubles per slot
   size_t d_res_slots_ = 0;
@@ -713,7 +715,8 @@ class Circuit {
     const qdc::SchedOptions so = sched_options();
     const std::vector<long> key = {(long)insts_.size(), all_dens ? 1L : 0L, so.n, so.n_loc, so.tile_bits, so.low_bits,
                                    so.max_tile_gates, so.min_tile_gates, so.group_bits, so.swap_min_pos, so.tile_strategy,
-                                   tc_active() ? 1L : 0L};
+                                   tc_active() ? 1L : 0L, (long)opt_auto_swap_pos_,
+                                   (peer_ok_ && opt_peer_ && opt_multi_swap_) ? 1L : 0L};
     if (key == plan_key_ && !plan_.steps.empty()) return;
     plan_key_ = key;
     std::vector<qdc::SchedInst> si(insts_.size());
@@ -724,8 +727,26 @@ class Circuit {
       si[i].q1 = insts_[i].pos1;
       si[i].skip = kind_is_dens(k) && !all_dens && !kind_is_diff_dens(k);
     }
-    qdc::Scheduler sch(si, sched_options());
-    plan_ = sch.run();
+    if (world_ > 1 && opt_auto_swap_pos_) {
+      // sharded: where the remap victims may sit is decided by the cost model of scheduler.hpp (every rank builds the
+      // same plan: the choice is a pure function of the program and the options)
+      qdc::CostModel cm;
+      cm.amp_bytes = (int)sizeof(cplx_t);
+      cm.vec_log2 = QDC_LV;
+      cm.merged = peer_ok_ && opt_peer_ && opt_multi_swap_;
+#ifdef QDC_F64
+      cm.tile_ms = 640;
+      cm.gate_ms = 70;
+      cm.shard_ms = 98.8;
+#else
+      cm.tile_ms = tc_active() ? 59 : 280;
+#endif
+      plan_ = qdc::schedule_best(si, so, cm, &chosen_swap_min_pos_);
+    } else {
+      qdc::Scheduler sch(si, so);
+      plan_ = sch.run();
+      chosen_swap_min_pos_ = so.swap_min_pos;
+    }
     plan_all_dens_ = all_dens;
     exec_p2_.assign(insts_.size(), -1);
     exec_p1_.assign(insts_.size(), -1);

@@ -139,6 +139,7 @@ QDC_EXPORT const char* qdc_circuit_set_option(qdc_circuit* c, const char* key, l
   else if (strcmp(key, "soa") == 0) c->impl.opt_soa_ = (int)value;    // f32 tile kernels: 0 selects the interleaved-layout kernels
   else if (strcmp(key, "peer") == 0) c->impl.opt_peer_ = (int)value;  // 0: force the NCCL send/recv exchange
   else if (strcmp(key, "multi_swap") == 0) c->impl.opt_multi_swap_ = (int)value;  // 0: one exchange per swapped qubit
+  else if (strcmp(key, "auto_swap_pos") == 0) c->impl.opt_auto_swap_pos_ = (int)value;  // 0: remap victims from positions >= 4 only
   else if (strcmp(key, "tc") == 0) {   // f32: tensor-core fused 6-qubit blocks (tc_exec.cuh)
 #ifdef QDC_F64
     if (value > 0) return qdc_errf("option \"tc\" exists in the f32 build only.");

@@ -487,4 +487,82 @@ class Scheduler {
   }
 };
 
+// ---- choice of the remap victims' lowest position by a cost model ------------------------------------------------
+// Victims at positions >= 4 exchange at the full NVLink rate, but on a qubit chain they cut an island off the low end of
+// the register (35-qubit brickwork on 8 ranks with 6-position windows: 205 passes instead of 189, 28 of them with <= 6
+// gates); victims from position 2 upwards keep the windows whole and pay with 32-byte runs in the exchange.  Both are
+// cheap to plan, so the executor plans every candidate and keeps the cheapest under this model (times in ms at the
+// scale of a 2^32-amplitude f32 shard on a B200; only their ratios matter):
+struct CostModel {
+  double tile_ms = 280;       // one fused pass, forward + reverse (tensor-core blocks: 59)
+  double gate_ms = 35;        // one streamed gate, forward + reverse
+  double shard_ms = 49.4;     // one full shard over NVLink at 695 GB/s per direction
+  int amp_bytes = 8;
+  int vec_log2 = 1;           // merged exchanges need positions >= this (circuit.cuh: multi_swap_ok)
+  bool merged = true;         // runs of swaps execute as one exchange (k_peer_multiswap)
+  // rate relative to 695 GB/s against the length of the contiguous runs: profiles/r1_exchange_bench_2gpu.txt (4 GiB
+  // halves: 0.73 / 0.56 / 0.46 / 0.60 for 64 / 32 / 16 / 8-byte runs) scaled by 0.7, what the 16 GiB halves of the 33-qubit
+  // run showed for 32-byte runs (268 GB/s per direction, profiles/r2_bench_2gpu_33q_tc_v2.json)
+  double run_efficiency(int pos) const {
+    const long run = (long)amp_bytes << pos;
+    return run >= 128 ? 1.0 : run >= 64 ? 0.51 : run >= 32 ? 0.39 : run >= 16 ? 0.32 : 0.42;
+  }
+};
+
+inline double plan_cost(const Plan& plan, const CostModel& m) {
+  double ms = 0;
+  const std::vector<Step>& st = plan.steps;
+  for (size_t i = 0; i < st.size(); i++) {
+    if (st[i].type == ST_TILE) ms += m.tile_ms;
+    else if (st[i].type == ST_GATE) ms += m.gate_ms;
+    else if (st[i].type == ST_SWAP) {
+      // the run of swaps the executor would merge (Circuit::swap_run): distinct global bits and positions, at most 3
+      int gb[3], lp[3], k = 0;
+      size_t j = i;
+      for (; j < st.size() && k < 3 && st[j].type == ST_SWAP; j++) {
+        bool clash = false;
+        for (int t = 0; t < k; t++) clash |= gb[t] == st[j].gbit || lp[t] == st[j].lpos;
+        if (clash) break;
+        gb[k] = st[j].gbit;
+        lp[k] = st[j].lpos;
+        k++;
+      }
+      bool can_merge = m.merged && k >= 2;
+      for (int t = 0; t < k; t++) can_merge &= lp[t] >= m.vec_log2;
+      if (!can_merge) k = 1;
+      int low = lp[0];
+      for (int t = 1; t < k; t++) low = lp[t] < low ? lp[t] : low;
+      const double frac = k == 1 ? 0.5 : (1.0 - 1.0 / (1 << k)) / 0.91;   // merged: 0.91 of the single-swap rate (4 x B200)
+      ms += 3.0 * frac * m.shard_ms / m.run_efficiency(low);            // state forward, state + adjoint in reverse
+      i += (size_t)(k - 1);
+    }
+  }
+  return ms;
+}
+
+// The plan of the cheapest candidate swap_min_pos in {opt.swap_min_pos, ..., 0} (ties: the highest position).
+inline Plan schedule_best(const std::vector<SchedInst>& insts, const SchedOptions& opt, const CostModel& m, int* chosen_min_pos) {
+  Plan best;
+  double best_ms = -1;
+  for (int mp = opt.swap_min_pos; mp >= 0; mp--) {
+    SchedOptions o = opt;
+    o.swap_min_pos = mp;
+    Scheduler sch(insts, o);
+    Plan p = sch.run();
+    if (!p.ok) continue;
+    const double ms = plan_cost(p, m);
+    if (best_ms < 0 || ms < best_ms * (1.0 - 1e-9)) {
+      best = p;
+      best_ms = ms;
+      if (chosen_min_pos) *chosen_min_pos = mp;
+    }
+  }
+  if (best_ms < 0) {   // nothing schedulable: report the failure of the default options
+    Scheduler sch(insts, opt);
+    best = sch.run();
+    if (chosen_min_pos) *chosen_min_pos = opt.swap_min_pos;
+  }
+  return best;
+}
+
 }  // namespace qdc
