@@ -64,6 +64,7 @@ _CIRCUIT_SIGNATURES = {
     "qdc_circuit_copy_state_to_host": (_err, [C.c_void_p, c_cplx_p]),
     "qdc_circuit_state_device_ptr": (_err, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "qdc_schedule_set_strategy": (_err, [C.c_int]),
+    "qdc_schedule_set_swap_min_pos": (_err, [C.c_int]),
     "qdc_circuit_save_state": (_err, [C.c_void_p, C.c_char_p]),
     "qdc_circuit_load_state": (_err, [C.c_void_p, C.c_char_p]),
     "qdc_circuit_state_layout": (_err, [C.c_void_p, C.POINTER(C.c_int)]),
@@ -167,7 +168,7 @@ def get_lib(precision: str) -> Lib:
 
 
 def schedule(instructions, n, n_loc=None, tile_bits=0, low_bits=0, max_tile_gates=0, all_densities=False,
-             precision="f32", tile_strategy=-1):
+             precision="f32", tile_strategy=-1, swap_min_pos=-1):
     """Run the C++ pass scheduler (pure host code) on `instructions`, a list of
     (kind, pos2[, pos1]) tuples; returns the int64 plan encoding of qdc_schedule."""
     lib = get_lib(precision)
@@ -178,6 +179,7 @@ def schedule(instructions, n, n_loc=None, tile_bits=0, low_bits=0, max_tile_gate
     out = np.zeros(cap, dtype=np.int64)
     n_out = C.c_size_t(0)
     lib.call("qdc_schedule_set_strategy", int(tile_strategy))
+    lib.call("qdc_schedule_set_swap_min_pos", int(swap_min_pos))   # -1 default, -2 cost model (sharded circuits)
     lib.call("qdc_schedule", n, n if n_loc is None else n_loc, tile_bits, low_bits, max_tile_gates,
              kinds.ctypes.data, p2.ctypes.data, p1.ctypes.data, len(instructions), int(all_densities),
              out.ctypes.data, cap, C.byref(n_out))

@@ -202,6 +202,16 @@ QDC_EXPORT const char* qdc_schedule_set_strategy(int tile_strategy) {
   return nullptr;
 }
 
+// Lowest position of the remap victims for the following qdc_schedule() calls: >= 0 fixed, -1 the library default (4),
+// -2 chosen by the cost model of scheduler.hpp (what a sharded Circuit does; tile_bits == 6 selects the tensor-core
+// pass time).  Lets the CPU suite check those plans without a device.
+static int g_schedule_swap_min_pos = -1;
+QDC_EXPORT const char* qdc_schedule_set_swap_min_pos(int swap_min_pos) {
+  if (swap_min_pos < -2) return qdc_errf("swap_min_pos must be >= -2.");
+  g_schedule_swap_min_pos = swap_min_pos;
+  return nullptr;
+}
+
 QDC_EXPORT const char* qdc_schedule(size_t n, size_t n_loc, int tile_bits, int low_bits, int max_tile_gates,
                                     const int* kinds, const size_t* pos2, const size_t* pos1, size_t count,
                                     int all_densities, int64_t* out, size_t cap, size_t* out_len) {
@@ -221,8 +231,18 @@ QDC_EXPORT const char* qdc_schedule(size_t n, size_t n_loc, int tile_bits, int l
   so.low_bits = low_bits;
   if (max_tile_gates > 0) so.max_tile_gates = max_tile_gates;
   if (g_schedule_tile_strategy >= 0) so.tile_strategy = g_schedule_tile_strategy;
-  qdc::Scheduler sch(si, so);
-  const qdc::Plan plan = sch.run();
+  if (g_schedule_swap_min_pos >= 0) so.swap_min_pos = g_schedule_swap_min_pos;
+  qdc::Plan plan;
+  if (g_schedule_swap_min_pos == -2) {
+    qdc::CostModel cm;
+    cm.amp_bytes = (int)sizeof(cplx_t);
+    cm.vec_log2 = QDC_LV;
+    if (tile_bits == 6) cm.tile_ms = 59;
+    plan = qdc::schedule_best(si, so, cm, nullptr);
+  } else {
+    qdc::Scheduler sch(si, so);
+    plan = sch.run();
+  }
   if (!plan.ok) return qdc_errf("the program cannot be scheduled on %zu local qubits per rank.", n_loc);
   std::vector<int64_t> enc;
   for (const qdc::Step& st : plan.steps) {

@@ -149,6 +149,9 @@ const char* qdc_circuit_last_profile(const qdc_circuit* c, int category, qdc_pro
  * and nbits x [position]; terminated by [-1, n, final_map[0..n-1]]. */
 const char* qdc_schedule_set_strategy(int tile_strategy); /* tiling of later qdc_schedule calls: 0 first-fit,
                                                            1 window growth, 2 + look-ahead, < 0 library default */
+const char* qdc_schedule_set_swap_min_pos(int swap_min_pos); /* lowest position of the remap victims of later qdc_schedule
+                                                           calls: >= 0 fixed, -1 library default (4), -2 chosen by the
+                                                           scheduler's cost model, as a sharded circuit does */
 const char* qdc_schedule(size_t n, size_t n_loc, int tile_bits, int low_bits, int max_tile_gates,
                          const int* kinds, const size_t* pos2, const size_t* pos1, size_t count,
                          int all_densities, int64_t* out, size_t capacity, size_t* out_len);

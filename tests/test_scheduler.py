@@ -65,10 +65,10 @@ def reference_results(o, const, var):
     return dens, cts_conj, grads
 
 
-def check_plan(pkg, o, const, var, n, n_loc, tile_bits, low_bits, max_tile_gates=0, tile_strategy=-1):
+def check_plan(pkg, o, const, var, n, n_loc, tile_bits, low_bits, max_tile_gates=0, tile_strategy=-1, swap_min_pos=-1):
     dens_ref, cts_conj, grads_ref = reference_results(o, const, var)
     enc = pkg._ffi.schedule(o.instructions, n, n_loc, tile_bits, low_bits, max_tile_gates,
-                            tile_strategy=tile_strategy)
+                            tile_strategy=tile_strategy, swap_min_pos=swap_min_pos)
     steps, final_map = op.decode_plan(enc)
     # structure
     seen = []
@@ -126,6 +126,33 @@ def test_sharded_plans_are_exact(pkg, case, g, tile_bits):
     n = 9
     o, const, var = make_case(case, n, np.random.default_rng(2))
     check_plan(pkg, o, const, var, n, n - g, tile_bits, 2 if tile_bits else 0)
+
+
+@pytest.mark.parametrize("case", ["brickwork", "vqse", "autodiff"])
+@pytest.mark.parametrize("g", [1, 2, 3])
+@pytest.mark.parametrize("swap_min_pos", [0, 1, 2, 3, -2])
+def test_sharded_plans_are_exact_wherever_the_remap_victims_sit(pkg, case, g, swap_min_pos):
+    """A sharded circuit lets a cost model choose the lowest position of its remap victims (scheduler.hpp:
+    schedule_best; -2 here): every candidate plan, and the chosen one, must be exact -- also with 6-position windows."""
+    n = 10
+    o, const, var = make_case(case, n, np.random.default_rng(3))
+    check_plan(pkg, o, const, var, n, n - g, 6, 0, max_tile_gates=32, swap_min_pos=swap_min_pos)
+
+
+def test_cost_model_keeps_the_windows_of_the_benchmark_plans_whole(pkg):
+    """33 / 35 qubits on 2 / 8 ranks, depth 100, 6-position windows: victims from position 4 upwards cut an island off
+    the low end of the chain (187 / 205 block passes); the cost model moves them down (175 / 192) with the same number of
+    exchanges.  34 qubits on 4 ranks keep position 4."""
+    for n, g, default_tiles, best_tiles, low in ((33, 1, 187, 175, 2), (34, 2, 190, 190, 4), (35, 3, 205, 192, 3)):
+        o = OracleCircuit.__new__(OracleCircuit)
+        o.instructions = []
+        brickwork(o, n, 100)
+        got = {}
+        for mp in (-1, -2):
+            steps, _ = op.decode_plan(pkg._ffi.schedule(o.instructions, n, n - g, 6, 0, 32, swap_min_pos=mp))
+            got[mp] = (sum(st["type"] == op.ST_TILE for st in steps), [st["lpos"] for st in steps if st["type"] == op.ST_SWAP])
+        assert got[-1][0] == default_tiles and got[-2][0] == best_tiles, (n, got[-1][0], got[-2][0])
+        assert len(got[-2][1]) == len(got[-1][1]) and min(got[-2][1]) == low, (n, got)
 
 
 def test_brickwork_swap_count_follows_the_light_cone(pkg):
