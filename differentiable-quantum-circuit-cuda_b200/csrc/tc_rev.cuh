@@ -9,7 +9,7 @@
 // state), follows on the host as G_W = H conj(W) (tc_host.hpp: tc_chain_rule_from_h) -- 64 x 64 matrices, in double.
 // H needs only the slices that the two block products need anyway, so one fill of shared memory feeds three GEMMs:
 //
-//     X' [128 x 64]  = R(W^dagger) [128 x 128] * X~ [128 x 64]           A = W slices (tensor memory / smem), B = X slices
+//     X' [128 x 64]  = R(W^dagger) [128 x 128] * X~ [128 x 64]           A = W slices (tensor memory), B = X slices
 //     Y'~[128 x 64]  = R(W^dagger) [128 x 128] * conj(Y)~ [128 x 64]     B = conj(Y) slices (imaginary rows negated)
 //     P' [128 x 128] += conj(Y)~ [128 x 64] * X~^T [64 x 128]            A, B = the same slices read along their rows
 //
